@@ -1,0 +1,193 @@
+/*
+ * nlo_cuda.h -- C ABI of libnlo_cuda.so: the B200 (sm_100a) Gauss-Newton / damped-LM
+ * normal-equation assembly + device-resident iteration loop for the Mahalanobis/NDT (6-DoF and
+ * 3-DoF planar) and reprojection-error pose minimizers.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its interface for this
+ * path is two C++ abstract classes (all citations relative to /root/reference/nonlinear_optimizer/)
+ *   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer.h:31-33   Solve(Options, vector<Correspondence>, Pose*)
+ *   reprojection_error_minimizer/reprojection_error_minimizer.h:30-32       Solve(Options, vector<Correspondence>, CameraIntrinsics, Pose*)
+ *   .../mahalanobis_distance_minimizer.h:29, reprojection_error_minimizer.h:20-22   SetLossFunction
+ * The C++ classes under nonlinear_optimizer_for_slam_b200/cxx/ keep those signatures and call
+ * the functions below; nothing here exposes C++, Eigen, torch or CUDA types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NLO_E* code on failure, never throws;
+ *     nlo_last_error(ctx) gives the message of the last failure on that context.
+ *   - all floating point data is IEEE double.  pose[16] is a 4x4 homogeneous transform in
+ *     COLUMN-major order (the memory of Eigen::Isometry3d, types.h:31).
+ *   - host arrays use the reference's record order: point[3n] xyz interleaved, mean[3n],
+ *     sqrt_info[9n] ROW-major 3x3 per correspondence (S(i,j) at 9k+3i+j), local_point[3n],
+ *     pixel[2n].  On the device they are repacked into SoA planes (DESIGN.md "HBM layout").
+ *   - H is the packed upper triangle in row-major order: 6-DoF 21 values
+ *     (0,0),(0,1)..(0,5),(1,1)..(5,5); 3-DoF 6 values.  g is J^T W r (6 or 3).
+ *   - a context owns one CUDA device + one stream; calls on one context are serialised by the
+ *     caller (same contract as the reference minimizers: not re-entrant per instance).
+ *   - there is no CPU fallback: without a usable CUDA device nlo_context_create fails.
+ */
+#ifndef NLO_CUDA_H_
+#define NLO_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NLO_API __attribute__((visibility("default")))
+#else
+#define NLO_API
+#endif
+
+enum {
+  NLO_OK = 0,
+  NLO_EINVAL = -1,   /* bad argument */
+  NLO_ECUDA = -2,    /* CUDA runtime error (message in nlo_last_error) */
+  NLO_ENOMEM = -3,   /* allocation failed */
+  NLO_ECOMM = -4,    /* NCCL / peer-memory communicator error */
+  NLO_ENUMERIC = -5  /* non-finite H, g or step met during a solve */
+};
+
+/* loss_function.h:20-77.  params: EXPONENTIAL {c1, c2}; HUBER {threshold}; CAUCHY {c}
+ * (Cauchy is an addition, Ceres convention rho = c^2 log(1+s/c^2)); NONE = plain least squares
+ * (the reference's loss_function_ == nullptr branch, ..._analytic.cc:44-48). */
+enum { NLO_LOSS_NONE = 0, NLO_LOSS_EXPONENTIAL = 1, NLO_LOSS_HUBER = 2, NLO_LOSS_CAUCHY = 3 };
+
+/* options.h:15-28 -- only the fields the reference's Solve() bodies read. */
+typedef struct nlo_solve_options {
+  int32_t max_iterations;     /* Options::max_iterations, default 40 */
+  int32_t reserved;
+  double parameter_tolerance; /* convergence_handle.parameter_tolerance, default 1e-6 */
+  double gradient_tolerance;  /* convergence_handle.gradient_tolerance, default 1e-6 */
+} nlo_solve_options;
+
+typedef struct nlo_solve_result {
+  int32_t iterations; /* the reference's `iteration` when the loop ends (printed as "iter:") */
+  int32_t status;     /* 0 ok, NLO_ENUMERIC if a non-finite value stopped the loop */
+  double final_cost;  /* the reference's `previous_cost` (printed as "COST:") */
+  double device_ms;   /* CUDA-event time of the device-resident loop on the context stream */
+} nlo_solve_result;
+
+/* Row width of the optional per-iteration trace (tests only):
+ *   6-DoF / reprojection: H21 | g6 | cost | t3 | q4(x,y,z,w) | lambda          = 36
+ *   3-DoF               : H6  | g3 | cost | t2 | R2 (row-major 4) | lambda     = 17
+ * pose and lambda are the values AFTER that iteration's update. */
+#define NLO_TRACE6 36
+#define NLO_TRACE3 17
+
+typedef struct nlo_context nlo_context;
+typedef struct nlo_problem nlo_problem;
+
+/* ---- context ---- */
+NLO_API int nlo_abi_version(void);
+NLO_API int nlo_context_create(int device, nlo_context** ctx);
+NLO_API int nlo_context_destroy(nlo_context* ctx);
+NLO_API const char* nlo_last_error(const nlo_context* ctx);
+/* sm_count, and the grid (CTAs) a single-problem assembly launch uses */
+NLO_API int nlo_context_info(const nlo_context* ctx, int* sm_count, int* assemble_grid);
+NLO_API int nlo_synchronize(nlo_context* ctx);
+/* SetLossFunction equivalent (…minimizer.h:29).  Applies to later assemble/solve calls. */
+NLO_API int nlo_set_loss(nlo_context* ctx, int kind, const double params[2]);
+
+/* pinned host memory for callers that want full-rate uploads */
+NLO_API int nlo_host_alloc(void** ptr, size_t bytes);
+NLO_API int nlo_host_free(void* ptr);
+
+/* ---- NDT / Mahalanobis correspondences (types.h:11-26) ---- */
+/* One problem of up to `capacity` correspondences. */
+NLO_API int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
+/* `num_problems` independent registrations; counts[k] correspondences each (BASELINE cfg5). */
+NLO_API int nlo_ndt_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts,
+                           nlo_problem** problem);
+/* Host -> device.  For a batched problem the arrays are the concatenation in problem order and
+ * n must equal the sum of counts. */
+NLO_API int nlo_ndt_upload(nlo_context* ctx, nlo_problem* problem, int64_t n, const double* point,
+                   const double* mean, const double* sqrt_info);
+/* Ingest the reference's AoS records in place (std::vector<Correspondence>::data()):
+ * `stride` bytes between records, byte offsets of point (3 doubles), mean (3 doubles) and
+ * sqrt_information (9 doubles, column-major if sqrt_info_col_major != 0 as Eigen stores it). */
+NLO_API int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* problem, int64_t n, const void* records,
+                       size_t stride, size_t offset_point, size_t offset_mean,
+                       size_t offset_sqrt_info, int sqrt_info_col_major);
+/* Device-side synthetic correspondences (bench / large-scale tests; no host copy):
+ * point i = counter-based PRNG(seed, global_index_offset + i) on the surfaces of the 7x5x2.5 m
+ * room of tests/simple_optimization_test.cc:170-204 expressed in the sensor frame of
+ * true_pose[16], associated with the cell of the dense voxel grid that contains the point under
+ * init_pose[16].  grid: origin[3], dims[3], voxel size, cell_mean[3*cells], cell_sqrt_info[9*cells]
+ * (row-major), cell_valid[cells] -- host arrays.  Points whose cell is invalid are resampled. */
+NLO_API int nlo_ndt_generate(nlo_context* ctx, nlo_problem* problem, int64_t n, uint64_t seed,
+                     int64_t global_index_offset, double noise_sigma, const double true_pose[16],
+                     const double init_pose[16], const double grid_origin[3],
+                     const int32_t grid_dims[3], double voxel_size, const double* cell_mean,
+                     const double* cell_sqrt_info, const uint8_t* cell_valid);
+/* Device -> host copy of correspondences [begin, end) in the host array convention (tests). */
+NLO_API int nlo_ndt_download(nlo_context* ctx, const nlo_problem* problem, int64_t begin, int64_t end,
+                     double* point, double* mean, double* sqrt_info);
+
+/* ---- reprojection correspondences (reprojection_error_minimizer/types.h:14-28) ---- */
+NLO_API int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
+/* intrinsics = {fx, fy, cx, cy, inv_fx, inv_fy} */
+NLO_API int nlo_reproj_upload(nlo_context* ctx, nlo_problem* problem, int64_t n,
+                      const double* local_point, const double* pixel,
+                      const double intrinsics[6]);
+
+NLO_API int nlo_problem_destroy(nlo_context* ctx, nlo_problem* problem);
+NLO_API int64_t nlo_problem_size(const nlo_problem* problem);
+
+/* ---- one assembly pass (parity tests, benchmarks) ----
+ * H, g, cost of correspondences [begin, end) at `pose` under the context's loss; with a
+ * communicator attached the sums are all-reduced over ranks.
+ *   ndt6   : ..._analytic.cc:12-52 + :159-185        H21, g6
+ *   ndt3   : ..._analytic_3dof.cc:33-68 + :110-139   H6,  g3 (caller chooses end; Solve uses floor(n/4)*4)
+ *   reproj : reprojection_error_minimizer_analytic.cc:31-63 + :107-162   H21, g6
+ * For a batched problem, `problem_index` selects the registration; otherwise pass 0. */
+NLO_API int nlo_ndt6_assemble(nlo_context* ctx, nlo_problem* problem, int32_t problem_index,
+                      const double pose[16], int64_t begin, int64_t end, double H21[21],
+                      double g[6], double* cost);
+NLO_API int nlo_ndt3_assemble(nlo_context* ctx, nlo_problem* problem, int32_t problem_index,
+                      const double pose[16], int64_t begin, int64_t end, double H6[6],
+                      double g[3], double* cost);
+NLO_API int nlo_reproj_assemble(nlo_context* ctx, nlo_problem* problem, int32_t problem_index,
+                        const double pose[16], int64_t begin, int64_t end, double H21[21],
+                        double g[6], double* cost);
+
+/* ---- device-resident solves ----
+ * pose: in = initial guess, out = optimized pose (3-DoF writes only x,y and the 2x2 block, as
+ * ..._analytic_3dof.cc:104-105).  trace may be NULL, else max_iterations * NLO_TRACE{6,3}
+ * doubles.  Returns NLO_OK also when the iteration cap is hit (the reference always returns
+ * true); NLO_ENUMERIC if a non-finite value was met.
+ *   ndt6   : ..._analytic.cc:54-157
+ *   ndt3   : ..._analytic_3dof.cc:14-108
+ *   reproj : reprojection_error_minimizer_analytic.cc:12-105 */
+NLO_API int nlo_ndt6_solve(nlo_context* ctx, nlo_problem* problem, const nlo_solve_options* options,
+                   double pose[16], nlo_solve_result* result, double* trace);
+NLO_API int nlo_ndt3_solve(nlo_context* ctx, nlo_problem* problem, const nlo_solve_options* options,
+                   double pose[16], nlo_solve_result* result, double* trace);
+NLO_API int nlo_reproj_solve(nlo_context* ctx, nlo_problem* problem, const nlo_solve_options* options,
+                     double pose[16], nlo_solve_result* result, double* trace);
+/* All registrations of a batched problem in one launch: poses[16*num_problems] in/out,
+ * results[num_problems].  No collective: problems are independent. */
+NLO_API int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* problem,
+                           const nlo_solve_options* options, double* poses,
+                           nlo_solve_result* results);
+
+/* ---- multi-GPU (one process per GPU; a large scan sharded by point range) ----
+ * With a communicator attached, every assemble/solve on the context sums its 28 (10 for 3-DoF)
+ * partial doubles over all ranks each iteration and every rank applies the identical update.
+ * NCCL flavour: rank 0 calls nlo_comm_unique_id and ships the 128 bytes to the others. */
+NLO_API int nlo_comm_unique_id(nlo_context* ctx, uint8_t id[128]);
+NLO_API int nlo_comm_init_nccl(nlo_context* ctx, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* Peer-memory flavour (NVLink/NVSwitch one-shot all-reduce fused into the iteration kernel):
+ * every rank exports a 64-byte handle, gathers all of them (rank order) and opens the peers. */
+NLO_API int nlo_comm_peer_export(nlo_context* ctx, uint8_t handle[64]);
+NLO_API int nlo_comm_peer_init(nlo_context* ctx, const uint8_t* handles, int32_t rank, int32_t nranks);
+NLO_API int nlo_comm_destroy(nlo_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLO_CUDA_H_ */

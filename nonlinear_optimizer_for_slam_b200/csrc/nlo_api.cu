@@ -1,0 +1,882 @@
+// nlo_api.cu -- the C ABI of include/nlo_cuda.h on top of the kernels in nlo_kernels.cu.
+//
+// Host-side responsibilities only: device memory for the SoA planes and the per-registration
+// state, upload/repack, CUDA-graph capture of the device-resident iteration loop, the optional
+// communicators (NCCL through dlopen, or CUDA-IPC peer memory for the fused one-shot all-reduce),
+// and the final pose / iteration-count read-back.  No arithmetic of the hot path runs on the host
+// and there is no CPU fallback.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/nlo_cuda.h"
+#include "nlo_internal.h"
+
+using namespace nlo;
+
+namespace {
+
+// ---- NCCL through dlopen (no link-time dependency; the symbols are only needed multi-GPU) ----
+struct NcclUniqueId {
+  char internal[128];
+};
+typedef void* NcclComm;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;      // ncclSum
+
+bool LoadNccl(NcclApi* api, std::string* err) {
+  if (api->handle != nullptr) return true;
+  const char* candidates[] = {"libnccl.so.2", "libnccl.so",
+                              "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+  void* h = nullptr;
+  for (const char* c : candidates) {
+    h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (h != nullptr) break;
+  }
+  if (h == nullptr) {
+    *err = std::string("dlopen(libnccl) failed: ") + dlerror();
+    return false;
+  }
+  api->handle = h;
+  api->GetUniqueId = reinterpret_cast<int (*)(NcclUniqueId*)>(dlsym(h, "ncclGetUniqueId"));
+  api->CommInitRank =
+      reinterpret_cast<int (*)(NcclComm*, int, NcclUniqueId, int)>(dlsym(h, "ncclCommInitRank"));
+  api->AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, NcclComm,
+                                            cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+  api->CommDestroy = reinterpret_cast<int (*)(NcclComm)>(dlsym(h, "ncclCommDestroy"));
+  api->GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  if (!api->GetUniqueId || !api->CommInitRank || !api->AllReduce || !api->CommDestroy) {
+    *err = "libnccl is missing a required symbol";
+    return false;
+  }
+  return true;
+}
+
+enum CommKind { kCommNone = 0, kCommNccl = 1, kCommPeer = 2 };
+
+constexpr size_t kPeerSlotBytes = 2 * kMaxRanks * 32 * sizeof(double);
+constexpr size_t kPeerFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
+constexpr size_t kPeerBufBytes = kPeerSlotBytes + kPeerFlagBytes;
+
+constexpr int kSmallDoubles = 8192;  // pinned + device scratch for poses / sums / results
+
+}  // namespace
+
+struct nlo_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  int grid_single = 0;
+  int loss_kind = NLO_LOSS_NONE;
+  double loss_params[2] = {0.0, 0.0};
+  std::string error;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+  double* host_small = nullptr;  // pinned
+  bool use_graph = true;
+  // communicator
+  int comm_kind = kCommNone;
+  int rank = 0, nranks = 1;
+  NcclApi nccl;
+  NcclComm nccl_comm = nullptr;
+  unsigned char* peer_buf = nullptr;  // local exchange buffer (exported over CUDA IPC)
+  void* peer_opened[kMaxRanks] = {nullptr};
+  PeerComm peer{};
+  unsigned long long* d_peer_seq = nullptr;
+  int* d_peer_error = nullptr;
+  int generation = 0;  // bumped whenever cached graphs become stale (loss / comm change)
+};
+
+struct nlo_problem {
+  int family = 0;  // 0 NDT, 1 reprojection
+  int num_planes = 0;
+  int64_t capacity = 0;  // padded, per plane
+  int64_t n = 0;
+  int num_problems = 1;
+  bool batched = false;
+  double* plane_block = nullptr;
+  double* planes[kNdtPlanes] = {nullptr};
+  std::vector<Range> h_ranges;
+  std::vector<int64_t> counts;
+  Range* d_ranges = nullptr;  // [num_problems + 1]; the last slot is the scratch range for assemble
+  State* d_states = nullptr;  // [num_problems + 1]
+  double* d_partials = nullptr;
+  unsigned int* d_tickets = nullptr;  // [num_problems + 1]
+  double* d_sums = nullptr;           // [(num_problems + 1) * 32]
+  double* d_poses = nullptr;          // [(num_problems + 1) * 16]
+  double* d_results = nullptr;        // [(num_problems + 1) * 4]
+  double* d_trace = nullptr;
+  size_t trace_doubles = 0;
+  double intrinsics[6] = {0, 0, 0, 0, 0, 0};
+  int grid_x = 1;
+  std::map<std::array<int64_t, 10>, cudaGraphExec_t> graphs;
+};
+
+namespace {
+
+int Fail(nlo_context* ctx, int code, const std::string& msg) {
+  if (ctx != nullptr) ctx->error = msg;
+  return code;
+}
+
+#define NLO_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      return Fail((ctx), (_e == cudaErrorMemoryAllocation) ? NLO_ENOMEM : NLO_ECUDA,     \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+    }                                                                                    \
+  } while (0)
+
+int EnsureStaging(nlo_context* ctx, size_t bytes) {
+  if (bytes <= ctx->staging_bytes) return NLO_OK;
+  if (ctx->staging != nullptr) {
+    NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NLO_CUDA(ctx, cudaFree(ctx->staging));
+    ctx->staging = nullptr;
+    ctx->staging_bytes = 0;
+  }
+  NLO_CUDA(ctx, cudaMalloc(&ctx->staging, bytes));
+  ctx->staging_bytes = bytes;
+  return NLO_OK;
+}
+
+void DropGraphs(nlo_problem* pr) {
+  for (auto& kv : pr->graphs) cudaGraphExecDestroy(kv.second);
+  pr->graphs.clear();
+}
+
+int64_t PadToTile(int64_t n) { return ((n + kTile - 1) / kTile) * kTile; }
+
+int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t* counts,
+                  bool batched, nlo_problem** out) {
+  if (ctx == nullptr || out == nullptr || num_problems < 1) return Fail(ctx, NLO_EINVAL, "bad argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  nlo_problem* pr = new nlo_problem();
+  pr->family = family;
+  pr->num_planes = (family == 0) ? kNdtPlanes : kReprojPlanes;
+  pr->num_problems = num_problems;
+  pr->batched = batched;
+  int64_t cursor = 0;
+  for (int k = 0; k < num_problems; ++k) {
+    if (counts[k] < 0) {
+      delete pr;
+      return Fail(ctx, NLO_EINVAL, "negative count");
+    }
+    pr->counts.push_back(counts[k]);
+    pr->h_ranges.push_back(Range{cursor, cursor + (batched ? counts[k] : 0)});
+    cursor += std::max<int64_t>(PadToTile(counts[k]), kTile);
+  }
+  pr->capacity = cursor;
+  const size_t plane_bytes = static_cast<size_t>(pr->capacity) * sizeof(double);
+  auto fail_free = [&](int code, const std::string& msg) {
+    nlo_problem_destroy(ctx, pr);
+    return Fail(ctx, code, msg);
+  };
+#define NLO_CUDA_P(expr)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return fail_free((_e == cudaErrorMemoryAllocation) ? NLO_ENOMEM : NLO_ECUDA,     \
+                       std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+  NLO_CUDA_P(cudaMalloc(&pr->plane_block, plane_bytes * pr->num_planes));
+  NLO_CUDA_P(cudaMemsetAsync(pr->plane_block, 0, plane_bytes * pr->num_planes, ctx->stream));
+  for (int k = 0; k < pr->num_planes; ++k) pr->planes[k] = pr->plane_block + static_cast<size_t>(k) * pr->capacity;
+  const int slots = num_problems + 1;
+  pr->grid_x = batched ? 1 : ctx->grid_single;
+  NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
+  NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
+  NLO_CUDA_P(cudaMalloc(&pr->d_partials,
+                        static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double) * (batched ? 1 : 1)));
+  NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_tickets, 0, slots * sizeof(unsigned int), ctx->stream));
+  NLO_CUDA_P(cudaMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_sums, 0, slots * 32 * sizeof(double), ctx->stream));
+  NLO_CUDA_P(cudaMalloc(&pr->d_poses, slots * 16 * sizeof(double)));
+  NLO_CUDA_P(cudaMalloc(&pr->d_results, slots * 4 * sizeof(double)));
+  NLO_CUDA_P(cudaMemcpyAsync(pr->d_ranges, pr->h_ranges.data(), num_problems * sizeof(Range),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA_P(cudaStreamSynchronize(ctx->stream));
+#undef NLO_CUDA_P
+  *out = pr;
+  return NLO_OK;
+}
+
+void PoseToRt(const double pose[16], double R[9], double t[3]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = pose[4 * c + r];
+  t[0] = pose[12];
+  t[1] = pose[13];
+  t[2] = pose[14];
+}
+
+IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
+  IterParams p;
+  memset(&p, 0, sizeof(p));
+  for (int k = 0; k < pr->num_planes; ++k) p.planes[k] = pr->planes[k];
+  p.partials = pr->d_partials;
+  p.loss_p0 = ctx->loss_params[0];
+  p.loss_p1 = ctx->loss_params[1];
+  for (int k = 0; k < 6; ++k) p.intrinsics[k] = pr->intrinsics[k];
+  p.parameter_tolerance = 1e-6;
+  p.gradient_tolerance = 1e-6;
+  p.max_iterations = 1;
+  p.iterations_in_kernel = 1;
+  p.use_peer = (ctx->comm_kind == kCommPeer) ? 1 : 0;
+  p.peer = ctx->peer;
+  return p;
+}
+
+int GridFor(nlo_context* ctx, int64_t begin, int64_t end) {
+  const int64_t tiles = (end + kTile - 1) / kTile - begin / kTile;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ctx->grid_single, tiles)));
+}
+
+int NcclAllReduceSums(nlo_context* ctx, double* sums) {
+  const int rc = ctx->nccl.AllReduce(sums, sums, 32, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+  if (rc != 0)
+    return Fail(ctx, NLO_ECOMM,
+                std::string("ncclAllReduce: ") + (ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "error"));
+  return NLO_OK;
+}
+
+int CheckPeerError(nlo_context* ctx) {
+  if (ctx->comm_kind != kCommPeer) return NLO_OK;
+  int err = 0;
+  NLO_CUDA(ctx, cudaMemcpy(&err, ctx->d_peer_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err != 0) return Fail(ctx, NLO_ECOMM, "peer all-reduce timed out waiting for a rank");
+  return NLO_OK;
+}
+
+int Assemble(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index, const double pose[16],
+             int64_t begin, int64_t end, double* H, int nh, double* g, int ng, double* cost) {
+  if (ctx == nullptr || pr == nullptr || pose == nullptr || H == nullptr || g == nullptr || cost == nullptr)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  if ((kind == kReproj) != (pr->family == 1)) return Fail(ctx, NLO_EINVAL, "problem family mismatch");
+  if (problem_index < 0 || problem_index >= pr->num_problems) return Fail(ctx, NLO_EINVAL, "bad problem_index");
+  const int64_t count = pr->batched ? pr->counts[problem_index] : pr->n;
+  if (begin < 0 || end < begin || end > count) return Fail(ctx, NLO_EINVAL, "bad [begin, end)");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int slot = pr->num_problems;  // scratch slot
+  const int64_t base = pr->h_ranges[problem_index].begin;
+  double* hs = ctx->host_small;
+  memcpy(hs, pose, 16 * sizeof(double));
+  Range* hr = reinterpret_cast<Range*>(hs + 16);
+  hr->begin = base + begin;
+  hr->end = base + end;
+  NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_poses + 16 * slot, hs, 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_ranges + slot, hr, sizeof(Range), cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA(ctx, LaunchInitStates(pr->d_states + slot, pr->d_poses + 16 * slot, 1, kind, ctx->stream));
+  IterParams p = BaseParams(ctx, pr);
+  p.ranges = pr->d_ranges + slot;
+  p.states = pr->d_states + slot;
+  p.tickets = pr->d_tickets + slot;
+  p.sums = pr->d_sums + 32 * slot;
+  p.mode = kModeAssemble;
+  const int grid_x = GridFor(ctx, hr->begin, hr->end);
+  NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, 1, ctx->stream));
+  if (ctx->comm_kind == kCommNccl) {
+    const int rc = NcclAllReduceSums(ctx, pr->d_sums + 32 * slot);
+    if (rc != NLO_OK) return rc;
+  }
+  double* out = hs + 64;
+  NLO_CUDA(ctx, cudaMemcpyAsync(out, pr->d_sums + 32 * slot, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(H, out, nh * sizeof(double));
+  memcpy(g, out + nh, ng * sizeof(double));
+  *cost = out[nh + ng];
+  return CheckPeerError(ctx);
+}
+
+// Enqueue the device-resident loop of one solve on the context stream.
+int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options& opt,
+                bool with_trace, int num_problems, int64_t begin_abs, int64_t end_abs) {
+  IterParams p = BaseParams(ctx, pr);
+  p.ranges = pr->d_ranges;
+  p.states = pr->d_states;
+  p.tickets = pr->d_tickets;
+  p.sums = pr->d_sums;
+  p.trace = with_trace ? pr->d_trace : nullptr;
+  p.parameter_tolerance = opt.parameter_tolerance;
+  p.gradient_tolerance = opt.gradient_tolerance;
+  p.max_iterations = opt.max_iterations;
+  const int64_t tiles = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
+  const bool in_cta_loop =
+      (ctx->comm_kind == kCommNone) && (pr->batched || tiles <= 16);
+  if (in_cta_loop) {
+    // whole loop inside one CTA per registration: a single launch
+    p.mode = kModeSolve;
+    p.iterations_in_kernel = opt.max_iterations;
+    NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, ctx->stream));
+    return NLO_OK;
+  }
+  const int grid_x = GridFor(ctx, begin_abs, end_abs);
+  for (int it = 0; it < opt.max_iterations; ++it) {
+    if (ctx->comm_kind == kCommNccl) {
+      p.mode = kModeAssemble;
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, num_problems, ctx->stream));
+      const int rc = NcclAllReduceSums(ctx, pr->d_sums);
+      if (rc != NLO_OK) return rc;
+      p.mode = kModeStepOnly;
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, ctx->stream));
+    } else {
+      p.mode = kModeSolve;
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, num_problems, ctx->stream));
+    }
+  }
+  return NLO_OK;
+}
+
+int RunLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options& opt,
+            bool with_trace, int num_problems, int64_t begin_abs, int64_t end_abs) {
+  // NCCL calls are left out of graph capture (their capture support depends on the library
+  // build); the other paths run as one CUDA graph so the loop needs a single host call.
+  const bool graph = ctx->use_graph && ctx->comm_kind != kCommNccl;
+  if (!graph) return EnqueueLoop(ctx, pr, kind, opt, with_trace, num_problems, begin_abs, end_abs);
+  int64_t ptol_bits, gtol_bits;
+  memcpy(&ptol_bits, &opt.parameter_tolerance, 8);
+  memcpy(&gtol_bits, &opt.gradient_tolerance, 8);
+  const std::array<int64_t, 10> key = {kind, ctx->loss_kind, ctx->comm_kind, opt.max_iterations,
+                                       with_trace ? 1 : 0, ctx->generation, ptol_bits, gtol_bits,
+                                       begin_abs * 4 + num_problems, end_abs};
+  auto it = pr->graphs.find(key);
+  if (it == pr->graphs.end()) {
+    if (pr->graphs.size() > 16) DropGraphs(pr);
+    cudaGraph_t graph_obj = nullptr;
+    NLO_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = EnqueueLoop(ctx, pr, kind, opt, with_trace, num_problems, begin_abs, end_abs);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph_obj);
+    if (rc != NLO_OK) {
+      if (graph_obj) cudaGraphDestroy(graph_obj);
+      return rc;
+    }
+    NLO_CUDA(ctx, e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph_obj, 0);
+    cudaGraphDestroy(graph_obj);
+    NLO_CUDA(ctx, e);
+    it = pr->graphs.emplace(key, exec).first;
+  }
+  NLO_CUDA(ctx, cudaGraphLaunch(it->second, ctx->stream));
+  return NLO_OK;
+}
+
+int Solve(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* options,
+          double* poses, nlo_solve_result* results, double* trace, bool batched_call) {
+  if (ctx == nullptr || pr == nullptr || options == nullptr || poses == nullptr || results == nullptr)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  if ((kind == kReproj) != (pr->family == 1)) return Fail(ctx, NLO_EINVAL, "problem family mismatch");
+  if (options->max_iterations < 0) return Fail(ctx, NLO_EINVAL, "max_iterations < 0");
+  if (batched_call != pr->batched) return Fail(ctx, NLO_EINVAL, "batched / single problem mismatch");
+  const int B = pr->num_problems;
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int trace_width = (kind == kNdt3) ? NLO_TRACE3 : NLO_TRACE6;
+  const bool with_trace = (trace != nullptr) && !pr->batched && options->max_iterations > 0;
+  if (with_trace) {
+    const size_t need = static_cast<size_t>(options->max_iterations) * trace_width;
+    if (need > pr->trace_doubles) {
+      if (pr->d_trace) NLO_CUDA(ctx, cudaFree(pr->d_trace));
+      pr->d_trace = nullptr;
+      NLO_CUDA(ctx, cudaMalloc(&pr->d_trace, need * sizeof(double)));
+      pr->trace_doubles = need;
+      DropGraphs(pr);
+    }
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_trace, 0, need * sizeof(double), ctx->stream));
+  }
+  // ranges of the registrations (single problem: [0, n) resp. floor(n/4)*4 for the 3-DoF path,
+  // ..._analytic_3dof.cc:33-36)
+  int64_t begin_abs = 0, end_abs = 0;
+  if (!pr->batched) {
+    Range r{0, pr->n};
+    if (kind == kNdt3) r.end = (pr->n / 4) * 4;
+    Range* hr = reinterpret_cast<Range*>(ctx->host_small + 32);
+    *hr = r;
+    NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_ranges, hr, sizeof(Range), cudaMemcpyHostToDevice, ctx->stream));
+    begin_abs = r.begin;
+    end_abs = r.end;
+  } else {
+    int64_t max_count = 0;
+    for (int64_t c : pr->counts) max_count = std::max(max_count, c);
+    end_abs = max_count;
+  }
+  NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_poses, poses, static_cast<size_t>(B) * 16 * sizeof(double),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA(ctx, LaunchInitStates(pr->d_states, pr->d_poses, B, kind, ctx->stream));
+  NLO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (options->max_iterations > 0) {
+    const int rc = RunLoop(ctx, pr, kind, *options, with_trace, B, begin_abs, end_abs);
+    if (rc != NLO_OK) return rc;
+  }
+  NLO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  NLO_CUDA(ctx, LaunchFinishStates(pr->d_states, pr->d_poses, pr->d_results, B, kind, ctx->stream));
+  std::vector<double> res(static_cast<size_t>(B) * 4);
+  NLO_CUDA(ctx, cudaMemcpyAsync(poses, pr->d_poses, static_cast<size_t>(B) * 16 * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpyAsync(res.data(), pr->d_results, static_cast<size_t>(B) * 4 * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (with_trace)
+    NLO_CUDA(ctx, cudaMemcpyAsync(trace, pr->d_trace,
+                                  static_cast<size_t>(options->max_iterations) * trace_width * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  NLO_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  int rc_all = NLO_OK;
+  for (int k = 0; k < B; ++k) {
+    results[k].iterations = static_cast<int32_t>(res[4 * k]);
+    results[k].status = (res[4 * k + 1] != 0.0) ? NLO_ENUMERIC : NLO_OK;
+    results[k].final_cost = res[4 * k + 2];
+    results[k].device_ms = ms;
+    if (results[k].status != NLO_OK) rc_all = NLO_ENUMERIC;
+  }
+  const int pe = CheckPeerError(ctx);
+  if (pe != NLO_OK) return pe;
+  if (rc_all != NLO_OK) return Fail(ctx, rc_all, "non-finite value met during the solve");
+  return NLO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nlo_abi_version(void) { return NLO_ABI_VERSION; }
+
+int nlo_context_create(int device, nlo_context** out) {
+  if (out == nullptr) return NLO_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return NLO_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return NLO_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NLO_ECUDA;
+  if (prop.major < 10) return NLO_ECUDA;  // sm_100a binary only; there is no fallback path
+  nlo_context* ctx = new nlo_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->grid_single = 2 * prop.multiProcessorCount;
+  const char* env = getenv("NLO_NO_GRAPH");
+  ctx->use_graph = !(env != nullptr && env[0] == '1');
+  const char* genv = getenv("NLO_GRID");
+  if (genv != nullptr && atoi(genv) > 0) ctx->grid_single = atoi(genv);
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+            cudaMallocHost(reinterpret_cast<void**>(&ctx->host_small), kSmallDoubles * sizeof(double)) == cudaSuccess &&
+            ConfigureKernels() == cudaSuccess;
+  if (!ok) {
+    nlo_context_destroy(ctx);
+    return NLO_ECUDA;
+  }
+  *out = ctx;
+  return NLO_OK;
+}
+
+int nlo_context_destroy(nlo_context* ctx) {
+  if (ctx == nullptr) return NLO_OK;
+  cudaSetDevice(ctx->device);
+  nlo_comm_destroy(ctx);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->host_small) cudaFreeHost(ctx->host_small);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NLO_OK;
+}
+
+const char* nlo_last_error(const nlo_context* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int nlo_context_info(const nlo_context* ctx, int* sm_count, int* assemble_grid) {
+  if (ctx == nullptr) return NLO_EINVAL;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (assemble_grid) *assemble_grid = ctx->grid_single;
+  return NLO_OK;
+}
+
+int nlo_synchronize(nlo_context* ctx) {
+  if (ctx == nullptr) return NLO_EINVAL;
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_set_loss(nlo_context* ctx, int kind, const double params[2]) {
+  if (ctx == nullptr) return NLO_EINVAL;
+  double p0 = params ? params[0] : 0.0, p1 = params ? params[1] : 0.0;
+  switch (kind) {
+    case NLO_LOSS_NONE: break;
+    case NLO_LOSS_EXPONENTIAL:  // loss_function.h:24-25: negative parameters are rejected
+      if (params == nullptr || p0 < 0.0 || p1 < 0.0) return Fail(ctx, NLO_EINVAL, "c1, c2 should be positive numbers");
+      break;
+    case NLO_LOSS_HUBER:  // loss_function.h:53-54
+      if (params == nullptr || !(p0 > 0.0)) return Fail(ctx, NLO_EINVAL, "threshold value should be larger than zero");
+      break;
+    case NLO_LOSS_CAUCHY:
+      if (params == nullptr || !(p0 > 0.0)) return Fail(ctx, NLO_EINVAL, "c should be larger than zero");
+      break;
+    default: return Fail(ctx, NLO_EINVAL, "unknown loss kind");
+  }
+  ctx->loss_kind = kind;
+  ctx->loss_params[0] = p0;
+  ctx->loss_params[1] = p1;
+  ctx->generation++;
+  return NLO_OK;
+}
+
+int nlo_host_alloc(void** ptr, size_t bytes) {
+  if (ptr == nullptr) return NLO_EINVAL;
+  return cudaMallocHost(ptr, bytes) == cudaSuccess ? NLO_OK : NLO_ENOMEM;
+}
+int nlo_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NLO_OK : NLO_ECUDA; }
+
+int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem) {
+  if (capacity < 0) return Fail(ctx, NLO_EINVAL, "negative capacity");
+  return CreateProblem(ctx, 0, 1, &capacity, false, problem);
+}
+
+int nlo_ndt_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts, nlo_problem** problem) {
+  if (counts == nullptr) return Fail(ctx, NLO_EINVAL, "null counts");
+  return CreateProblem(ctx, 0, num_problems, counts, true, problem);
+}
+
+int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem) {
+  if (capacity < 0) return Fail(ctx, NLO_EINVAL, "negative capacity");
+  return CreateProblem(ctx, 1, 1, &capacity, false, problem);
+}
+
+int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
+  if (pr == nullptr) return NLO_OK;
+  if (ctx != nullptr) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  DropGraphs(pr);
+  cudaFree(pr->plane_block);
+  cudaFree(pr->d_ranges);
+  cudaFree(pr->d_states);
+  cudaFree(pr->d_partials);
+  cudaFree(pr->d_tickets);
+  cudaFree(pr->d_sums);
+  cudaFree(pr->d_poses);
+  cudaFree(pr->d_results);
+  cudaFree(pr->d_trace);
+  delete pr;
+  return NLO_OK;
+}
+
+int64_t nlo_problem_size(const nlo_problem* pr) { return pr ? pr->n : -1; }
+
+int nlo_ndt_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* point, const double* mean,
+                   const double* sqrt_info) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (n < 0 || (n > 0 && (point == nullptr || mean == nullptr || sqrt_info == nullptr)))
+    return Fail(ctx, NLO_EINVAL, "null array");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  int64_t total = 0;
+  for (int64_t c : pr->counts) total += c;
+  if (pr->batched ? (n != total) : (n > pr->counts[0])) return Fail(ctx, NLO_EINVAL, "n does not fit the problem");
+  const size_t bytes = static_cast<size_t>(n) * 15 * sizeof(double);
+  const size_t extra = pr->batched ? (pr->num_problems + 1) * sizeof(int64_t) : 0;
+  int rc = EnsureStaging(ctx, bytes + extra + 256);
+  if (rc != NLO_OK) return rc;
+  double* s_point = static_cast<double*>(ctx->staging);
+  double* s_mean = s_point + 3 * n;
+  double* s_sqrt = s_mean + 3 * n;
+  if (n > 0) {
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_point, point, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_mean, mean, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_sqrt, sqrt_info, 9 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!pr->batched) {
+    NLO_CUDA(ctx, LaunchPackNdt(s_point, s_mean, s_sqrt, n, pr->planes, 0, ctx->stream));
+    pr->n = n;
+    pr->h_ranges[0] = Range{0, n};
+  } else {
+    std::vector<int64_t> prefix(pr->num_problems + 1, 0);
+    for (int k = 0; k < pr->num_problems; ++k) prefix[k + 1] = prefix[k] + pr->counts[k];
+    int64_t* d_prefix = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(ctx->staging) +
+                                                   ((bytes + 255) / 256) * 256);
+    NLO_CUDA(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * sizeof(int64_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, LaunchPackNdtBatched(s_point, s_mean, s_sqrt, n, d_prefix, pr->d_ranges,
+                                       pr->num_problems, pr->planes, ctx->stream));
+    pr->n = n;
+    NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // prefix vector goes out of scope
+  }
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
+                       size_t offset_point, size_t offset_mean, size_t offset_sqrt_info, int col_major) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (n < 0 || n > pr->counts[0] || (n > 0 && records == nullptr)) return Fail(ctx, NLO_EINVAL, "bad n / records");
+  if (stride % 8 != 0 || offset_point % 8 != 0 || offset_mean % 8 != 0 || offset_sqrt_info % 8 != 0)
+    return Fail(ctx, NLO_EINVAL, "record layout must be 8-byte aligned");
+  if (offset_point + 24 > stride || offset_mean + 24 > stride || offset_sqrt_info + 72 > stride)
+    return Fail(ctx, NLO_EINVAL, "field outside the record");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = static_cast<size_t>(n) * stride;
+  int rc = EnsureStaging(ctx, bytes + 256);
+  if (rc != NLO_OK) return rc;
+  if (n > 0) {
+    NLO_CUDA(ctx, cudaMemcpyAsync(ctx->staging, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, LaunchPackNdtAos(static_cast<const unsigned char*>(ctx->staging), n, stride, offset_point,
+                                   offset_mean, offset_sqrt_info, col_major, pr->planes, ctx->stream));
+  }
+  pr->n = n;
+  pr->h_ranges[0] = Range{0, n};
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_ndt_generate(nlo_context* ctx, nlo_problem* pr, int64_t n, uint64_t seed, int64_t global_index_offset,
+                     double noise_sigma, const double true_pose[16], const double init_pose[16],
+                     const double grid_origin[3], const int32_t grid_dims[3], double voxel_size,
+                     const double* cell_mean, const double* cell_sqrt_info, const uint8_t* cell_valid) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (n < 0 || n > pr->counts[0]) return Fail(ctx, NLO_EINVAL, "n exceeds capacity");
+  if (!true_pose || !init_pose || !grid_origin || !grid_dims || !cell_mean || !cell_sqrt_info || !cell_valid ||
+      !(voxel_size > 0.0))
+    return Fail(ctx, NLO_EINVAL, "null / bad grid argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t cells = static_cast<size_t>(grid_dims[0]) * grid_dims[1] * grid_dims[2];
+  const size_t bytes = cells * (12 * sizeof(double) + 1) + 512;
+  int rc = EnsureStaging(ctx, bytes);
+  if (rc != NLO_OK) return rc;
+  double* d_mean = static_cast<double*>(ctx->staging);
+  double* d_sqrt = d_mean + 3 * cells;
+  unsigned char* d_valid = reinterpret_cast<unsigned char*>(d_sqrt + 9 * cells);
+  NLO_CUDA(ctx, cudaMemcpyAsync(d_mean, cell_mean, 3 * cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpyAsync(d_sqrt, cell_sqrt_info, 9 * cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpyAsync(d_valid, cell_valid, cells, cudaMemcpyHostToDevice, ctx->stream));
+  GenerateParams g;
+  memset(&g, 0, sizeof(g));
+  for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k];
+  g.n = n;
+  g.seed = seed;
+  g.index_offset = global_index_offset;
+  g.noise_sigma = noise_sigma;
+  PoseToRt(true_pose, g.R_true, g.t_true);
+  PoseToRt(init_pose, g.R_init, g.t_init);
+  for (int k = 0; k < 3; ++k) {
+    g.origin[k] = grid_origin[k];
+    g.dims[k] = grid_dims[k];
+  }
+  g.inv_voxel = 1.0 / voxel_size;
+  g.reach = std::min(4, static_cast<int>(std::ceil(1.0 / voxel_size)));
+  g.cell_mean = d_mean;
+  g.cell_sqrt_info = d_sqrt;
+  g.cell_valid = d_valid;
+  NLO_CUDA(ctx, LaunchGenerateNdt(g, ctx->stream));
+  pr->n = n;
+  pr->h_ranges[0] = Range{0, n};
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_ndt_download(nlo_context* ctx, const nlo_problem* pr, int64_t begin, int64_t end, double* point,
+                     double* mean, double* sqrt_info) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (begin < 0 || end < begin || end > pr->n) return Fail(ctx, NLO_EINVAL, "bad [begin, end)");
+  if (!point || !mean || !sqrt_info) return Fail(ctx, NLO_EINVAL, "null array");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = end - begin;
+  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 15 * sizeof(double) + 256);
+  if (rc != NLO_OK) return rc;
+  double* s_point = static_cast<double*>(ctx->staging);
+  double* s_mean = s_point + 3 * n;
+  double* s_sqrt = s_mean + 3 * n;
+  NLO_CUDA(ctx, LaunchUnpackNdt(const_cast<double* const*>(pr->planes), begin, end, s_point, s_mean, s_sqrt, ctx->stream));
+  if (n > 0) {
+    NLO_CUDA(ctx, cudaMemcpyAsync(point, s_point, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(mean, s_mean, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(sqrt_info, s_sqrt, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_reproj_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* local_point, const double* pixel,
+                      const double intrinsics[6]) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 1) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (n < 0 || n > pr->counts[0] || intrinsics == nullptr || (n > 0 && (!local_point || !pixel)))
+    return Fail(ctx, NLO_EINVAL, "bad argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 5 * sizeof(double) + 256);
+  if (rc != NLO_OK) return rc;
+  double* s_point = static_cast<double*>(ctx->staging);
+  double* s_pixel = s_point + 3 * n;
+  if (n > 0) {
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_point, local_point, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_pixel, pixel, 2 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, LaunchPackReproj(s_point, s_pixel, n, pr->planes, ctx->stream));
+  }
+  for (int k = 0; k < 6; ++k) pr->intrinsics[k] = intrinsics[k];
+  pr->n = n;
+  pr->h_ranges[0] = Range{0, n};
+  DropGraphs(pr);  // intrinsics are baked into captured launches
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
+int nlo_ndt6_assemble(nlo_context* ctx, nlo_problem* pr, int32_t problem_index, const double pose[16], int64_t begin,
+                      int64_t end, double H21[21], double g[6], double* cost) {
+  return Assemble(ctx, pr, kNdt6, problem_index, pose, begin, end, H21, 21, g, 6, cost);
+}
+int nlo_ndt3_assemble(nlo_context* ctx, nlo_problem* pr, int32_t problem_index, const double pose[16], int64_t begin,
+                      int64_t end, double H6[6], double g[3], double* cost) {
+  return Assemble(ctx, pr, kNdt3, problem_index, pose, begin, end, H6, 6, g, 3, cost);
+}
+int nlo_reproj_assemble(nlo_context* ctx, nlo_problem* pr, int32_t problem_index, const double pose[16],
+                        int64_t begin, int64_t end, double H21[21], double g[6], double* cost) {
+  return Assemble(ctx, pr, kReproj, problem_index, pose, begin, end, H21, 21, g, 6, cost);
+}
+
+int nlo_ndt6_solve(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double pose[16],
+                   nlo_solve_result* result, double* trace) {
+  return Solve(ctx, pr, kNdt6, options, pose, result, trace, false);
+}
+int nlo_ndt3_solve(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double pose[16],
+                   nlo_solve_result* result, double* trace) {
+  return Solve(ctx, pr, kNdt3, options, pose, result, trace, false);
+}
+int nlo_reproj_solve(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double pose[16],
+                     nlo_solve_result* result, double* trace) {
+  return Solve(ctx, pr, kReproj, options, pose, result, trace, false);
+}
+int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double* poses,
+                           nlo_solve_result* results) {
+  return Solve(ctx, pr, kNdt6, options, poses, results, nullptr, true);
+}
+
+// ---- communicators ----
+int nlo_comm_unique_id(nlo_context* ctx, uint8_t id[128]) {
+  if (ctx == nullptr || id == nullptr) return NLO_EINVAL;
+  std::string err;
+  if (!LoadNccl(&ctx->nccl, &err)) return Fail(ctx, NLO_ECOMM, err);
+  NcclUniqueId uid;
+  const int rc = ctx->nccl.GetUniqueId(&uid);
+  if (rc != 0) return Fail(ctx, NLO_ECOMM, "ncclGetUniqueId failed");
+  memcpy(id, uid.internal, 128);
+  return NLO_OK;
+}
+
+int nlo_comm_init_nccl(nlo_context* ctx, const uint8_t id[128], int32_t rank, int32_t nranks) {
+  if (ctx == nullptr || id == nullptr || nranks < 1 || rank < 0 || rank >= nranks) return Fail(ctx, NLO_EINVAL, "bad rank");
+  if (ctx->comm_kind != kCommNone) return Fail(ctx, NLO_EINVAL, "a communicator is already attached");
+  std::string err;
+  if (!LoadNccl(&ctx->nccl, &err)) return Fail(ctx, NLO_ECOMM, err);
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  const int rc = ctx->nccl.CommInitRank(&ctx->nccl_comm, nranks, uid, rank);
+  if (rc != 0)
+    return Fail(ctx, NLO_ECOMM, std::string("ncclCommInitRank: ") +
+                                    (ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "error"));
+  ctx->comm_kind = kCommNccl;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->generation++;
+  return NLO_OK;
+}
+
+int nlo_comm_peer_export(nlo_context* ctx, uint8_t handle[64]) {
+  if (ctx == nullptr || handle == nullptr) return NLO_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->peer_buf == nullptr) {
+    NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->peer_buf), kPeerBufBytes));
+    NLO_CUDA(ctx, cudaMemset(ctx->peer_buf, 0, kPeerBufBytes));
+    NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_peer_seq), sizeof(unsigned long long)));
+    NLO_CUDA(ctx, cudaMemset(ctx->d_peer_seq, 0, sizeof(unsigned long long)));
+    NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_peer_error), sizeof(int)));
+    NLO_CUDA(ctx, cudaMemset(ctx->d_peer_error, 0, sizeof(int)));
+    NLO_CUDA(ctx, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  NLO_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_buf));
+  memcpy(handle, &h, 64);
+  return NLO_OK;
+}
+
+int nlo_comm_peer_init(nlo_context* ctx, const uint8_t* handles, int32_t rank, int32_t nranks) {
+  if (ctx == nullptr || handles == nullptr || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
+    return Fail(ctx, NLO_EINVAL, "bad rank / nranks (max 8)");
+  if (ctx->comm_kind != kCommNone) return Fail(ctx, NLO_EINVAL, "a communicator is already attached");
+  if (ctx->peer_buf == nullptr) return Fail(ctx, NLO_EINVAL, "call nlo_comm_peer_export first");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  PeerComm pc;
+  memset(&pc, 0, sizeof(pc));
+  pc.rank = rank;
+  pc.nranks = nranks;
+  for (int r = 0; r < nranks; ++r) {
+    unsigned char* base = nullptr;
+    if (r == rank) {
+      base = ctx->peer_buf;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * r, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return Fail(ctx, NLO_ECOMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      ctx->peer_opened[r] = ptr;
+      base = static_cast<unsigned char*>(ptr);
+    }
+    pc.slots[r] = reinterpret_cast<double*>(base);
+    pc.flags[r] = reinterpret_cast<unsigned long long*>(base + kPeerSlotBytes);
+  }
+  pc.seq = ctx->d_peer_seq;
+  pc.error = ctx->d_peer_error;
+  ctx->peer = pc;
+  ctx->comm_kind = kCommPeer;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->generation++;
+  return NLO_OK;
+}
+
+int nlo_comm_destroy(nlo_context* ctx) {
+  if (ctx == nullptr) return NLO_EINVAL;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm_kind == kCommNccl && ctx->nccl_comm != nullptr) {
+    ctx->nccl.CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (ctx->peer_opened[r] != nullptr) {
+      cudaIpcCloseMemHandle(ctx->peer_opened[r]);
+      ctx->peer_opened[r] = nullptr;
+    }
+  }
+  if (ctx->peer_buf) { cudaFree(ctx->peer_buf); ctx->peer_buf = nullptr; }
+  if (ctx->d_peer_seq) { cudaFree(ctx->d_peer_seq); ctx->d_peer_seq = nullptr; }
+  if (ctx->d_peer_error) { cudaFree(ctx->d_peer_error); ctx->d_peer_error = nullptr; }
+  ctx->comm_kind = kCommNone;
+  ctx->rank = 0;
+  ctx->nranks = 1;
+  ctx->generation++;
+  return NLO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// nlo_internal.h -- structures shared by the kernels (nlo_kernels.cu) and the C ABI (nlo_api.cu).
+#ifndef NLO_INTERNAL_H_
+#define NLO_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nlo {
+
+enum Kind : int { kNdt6 = 0, kNdt3 = 1, kReproj = 2 };
+
+constexpr int kTile = 256;            // correspondences per pipeline stage = consumer threads
+constexpr int kConsumerWarps = kTile / 32;
+constexpr int kThreads = kTile;       // thread 0 doubles as the TMA producer
+constexpr int kNdtPlanes = 15;        // x y z | mx my mz | s00 s01 s02 s10 s11 s12 s20 s21 s22
+constexpr int kReprojPlanes = 5;      // X Y Z | u v
+constexpr int kAcc6 = 28;             // 21 H + 6 g + cost
+constexpr int kAcc3 = 10;             // 6 H + 3 g + cost
+constexpr int kMaxRanks = 8;
+
+// Per-registration optimisation state, resident in HBM for the whole solve.
+//   6-DoF / reprojection: t[3], q[4] (x,y,z,w), R = row-major rotation of q.
+//   3-DoF: t[0..1], R[0..3] = row-major 2x2 (the reference keeps an Isometry2d, no quaternion).
+struct State {
+  double t[3];
+  double q[4];
+  double R[9];
+  double lambda;
+  double previous_cost;
+  int iteration;
+  int done;
+  int status;
+  int pad;
+};
+
+struct Range {
+  int64_t begin;  // absolute index into the planes
+  int64_t end;
+};
+
+// One-shot all-reduce over peer-mapped buffers (NVLink / NVSwitch).
+//   slots[r] points into rank r's exchange buffer: [2 parities][kMaxRanks sources][32 doubles]
+//   flags[r] points into rank r's flag array:       [2 parities][kMaxRanks sources] (uint64 seq)
+struct PeerComm {
+  int rank;
+  int nranks;
+  double* slots[kMaxRanks];
+  unsigned long long* flags[kMaxRanks];
+  unsigned long long* seq;  // local, device: exchange sequence number (monotonic)
+  int* error;               // local, device: set to 1 if a wait timed out
+};
+
+enum Mode : int {
+  kModeSolve = 0,     // assemble + (last CTA) reduce + damped step + state update
+  kModeAssemble = 1,  // assemble + reduce, canonical sums written to sums_out, no step
+  kModeStepOnly = 2   // no assembly: read reduced canonical sums from sums_in and step (NCCL path)
+};
+
+struct IterParams {
+  const double* planes[kNdtPlanes];
+  const Range* ranges;  // [num_problems]
+  State* states;        // [num_problems]
+  double* partials;     // [num_problems][grid.x][nacc]
+  unsigned int* tickets;  // [num_problems]
+  double* sums;           // [num_problems][32] canonical H|g|cost (out for assemble, in for step-only)
+  double* trace;          // nullable: [num_problems][max_iterations][trace_width]
+  double loss_p0, loss_p1;
+  double intrinsics[6];
+  double parameter_tolerance, gradient_tolerance;
+  int max_iterations;
+  int iterations_in_kernel;  // > 1 only when grid.x == 1 (whole loop inside one CTA)
+  int mode;
+  int use_peer;
+  PeerComm peer;
+};
+
+// Launchers (nlo_kernels.cu).  grid_x CTAs per registration, num_problems registrations.
+cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
+                            cudaStream_t stream);
+cudaError_t ConfigureKernels();
+size_t IterationSmemBytes(int kind);
+
+// Small utility kernels.
+cudaError_t LaunchInitStates(State* states, const double* poses16, int num_problems, int kind,
+                             cudaStream_t stream);
+cudaError_t LaunchFinishStates(const State* states, double* poses16, double* results4,
+                               int num_problems, int kind, cudaStream_t stream);
+cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
+                          int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
+                          cudaStream_t stream);
+cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
+                                 int64_t n_total, const int64_t* src_prefix,
+                                 const Range* ranges, int num_problems,
+                                 double* const planes[kNdtPlanes], cudaStream_t stream);
+cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t stride,
+                             size_t off_point, size_t off_mean, size_t off_sqrt, int col_major,
+                             double* const planes[kNdtPlanes], cudaStream_t stream);
+cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int64_t end,
+                            double* point, double* mean, double* sqrt_info, cudaStream_t stream);
+cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
+                             double* const planes[kReprojPlanes], cudaStream_t stream);
+
+struct GenerateParams {
+  double* planes[kNdtPlanes];
+  int64_t n;
+  uint64_t seed;
+  int64_t index_offset;
+  double noise_sigma;
+  double R_true[9], t_true[3];  // sensor -> world (row-major R)
+  double R_init[9], t_init[3];
+  double origin[3];
+  int dims[3];
+  double inv_voxel;
+  int reach;  // neighbour cells scanned for the nearest-mean fallback: ceil(1 m / voxel)
+  const double* cell_mean;
+  const double* cell_sqrt_info;
+  const unsigned char* cell_valid;
+};
+cudaError_t LaunchGenerateNdt(const GenerateParams& p, cudaStream_t stream);
+
+}  // namespace nlo
+
+#endif  // NLO_INTERNAL_H_

@@ -1,0 +1,715 @@
+// nlo_kernels.cu -- sm_100a kernels of the hot path.
+//
+// gn_iteration_kernel<KIND, LOSS>: one Gauss-Newton / damped-LM iteration (or, for a registration
+// that fits one CTA, the whole loop) of one or many registrations:
+//
+//   HBM SoA planes --cp.async.bulk (TMA 1-D), mbarrier full/empty ring--> shared memory stages
+//     --> 8 consumer warps: residual, analytic Jacobian terms, robust-loss weight, 28 (10) fp64
+//         register accumulators per thread
+//     --> warp shuffle -> shared -> per-CTA partial -> (last CTA by ticket) fixed-order fp64 sum
+//     --> [peer-memory all-reduce over NVLink when sharded across GPUs]
+//     --> one thread: rotate to the canonical H|g, damp, 6x6 / 3x3 solve, pose update,
+//         convergence tests, lambda schedule, trace row; state stays in HBM for the next launch.
+//
+// Replaces the per-iteration loops of (paths relative to /root/reference/nonlinear_optimizer/)
+//   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_analytic.cc:92-149
+//   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_analytic_3dof.cc:29-99
+//   reprojection_error_minimizer/reprojection_error_minimizer_analytic.cc:26-100
+// and their SIMD / thread-pool twins (..._analytic_simd.cc:55-76,114-177).
+#include <cstdio>
+
+#include "nlo_device.cuh"
+
+namespace nlo {
+
+// ------------------------------------------------------------------ PTX helpers (mbarrier, TMA)
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void MbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(SmemAddr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+  while (!MbarTryWait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (TMA engine, UBLKCP in SASS).
+__device__ __forceinline__ void BulkLoad(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(SmemAddr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(SmemAddr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void FenceBarrierInit() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long GlobalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int KIND>
+struct KindTraits;
+template <>
+struct KindTraits<kNdt6> {
+  static constexpr int kPlanes = kNdtPlanes, kAcc = kAcc6, kStages = 3, kTrace = 36;
+};
+template <>
+struct KindTraits<kNdt3> {
+  static constexpr int kPlanes = kNdtPlanes, kAcc = kAcc3, kStages = 3, kTrace = 17;
+};
+template <>
+struct KindTraits<kReproj> {
+  static constexpr int kPlanes = kReprojPlanes, kAcc = kAcc6, kStages = 4, kTrace = 36;
+};
+
+template <int KIND>
+struct SmemLayout {
+  using T = KindTraits<KIND>;
+  double stages[T::kStages][T::kPlanes][kTile];
+  double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
+  double total[32];            // reduced (raw, then canonical) sums
+  double pose[12];             // R (9) | t (3) broadcast for the in-CTA loop
+  uint64_t full[T::kStages];
+  uint64_t empty[T::kStages];
+  int flag;
+};
+
+template <int KIND>
+constexpr size_t SmemBytes() {
+  return sizeof(SmemLayout<KIND>) + 128;
+}
+
+// One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
+// finalising CTA.  Sum order is rank 0..n-1 on every rank => bit-identical results everywhere.
+__device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc) {
+  const int tid = threadIdx.x;
+  const unsigned long long seq = *pc.seq + 1;
+  const int parity = static_cast<int>(seq & 1ULL);
+  const int slot = (parity * kMaxRanks + pc.rank) * 32;
+  if (tid < nacc) {
+    const double v = total[tid];
+    for (int r = 0; r < pc.nranks; ++r) {
+      volatile double* dst = pc.slots[r] + slot;
+      dst[tid] = v;
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < pc.nranks) {
+    volatile unsigned long long* f = pc.flags[tid] + parity * kMaxRanks + pc.rank;
+    *f = seq;
+  }
+  if (tid < pc.nranks) {
+    volatile unsigned long long* f = pc.flags[pc.rank] + parity * kMaxRanks + tid;
+    const unsigned long long start = GlobalTimerNs();
+    while (*f < seq) {
+      if (GlobalTimerNs() - start > 5000000000ULL) {  // 5 s: a peer died; fail instead of hanging
+        *pc.error = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < nacc) {
+    double s = 0.0;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const volatile double* src = pc.slots[pc.rank] + (parity * kMaxRanks + r) * 32;
+      s += src[tid];
+    }
+    total[tid] = s;
+  }
+  if (tid == 0) *pc.seq = seq;
+  __syncthreads();
+}
+
+template <int KIND, int LOSS>
+__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
+  using T = KindTraits<KIND>;
+  constexpr int NACC = T::kAcc;
+  constexpr int NPLANES = T::kPlanes;
+  constexpr int STAGES = T::kStages;
+  constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(double);
+
+  extern __shared__ unsigned char smem_raw[];
+  SmemLayout<KIND>& sm = *reinterpret_cast<SmemLayout<KIND>*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int problem = blockIdx.y;
+  const int grid_x = gridDim.x;
+  State* st = p.states + problem;
+
+  if (p.mode != kModeStepOnly) {
+    if (tid == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        MbarInit(&sm.full[s], 1);
+        MbarInit(&sm.empty[s], kConsumerWarps);
+      }
+      FenceBarrierInit();
+    }
+  }
+  __syncthreads();
+
+  const Range range = p.ranges[problem];
+  const int64_t tile_lo = range.begin / kTile;
+  const int64_t tile_hi = (range.end + kTile - 1) / kTile;
+  // tiles of this CTA: tile_lo + blockIdx.x + m * grid_x
+  const int64_t span = tile_hi - tile_lo;
+  const int my_tiles =
+      (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
+
+  uint32_t ring = 0;  // tiles consumed so far by this CTA (keeps mbarrier phases across iterations)
+
+  for (int it = 0; it < p.iterations_in_kernel; ++it) {
+    if (st->done) break;  // uniform: state is only written behind a __syncthreads / launch boundary
+
+    if (p.mode != kModeStepOnly) {
+      double acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+
+      {
+        // Producer duty (thread 0): keep STAGES-1 tiles in flight ahead of the tile being consumed.
+        auto issue_tile = [&](int m) {
+          const uint32_t k = ring + m;
+          const int s = k % STAGES;
+          const uint32_t phase = (k / STAGES) & 1u;
+          MbarWait(&sm.empty[s], phase ^ 1u);
+          MbarExpectTx(&sm.full[s], kStageBytes);
+          const int64_t first = (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile;
+#pragma unroll
+          for (int pl = 0; pl < NPLANES; ++pl)
+            BulkLoad(&sm.stages[s][pl][0], p.planes[pl] + first, kTile * sizeof(double),
+                     &sm.full[s]);
+        };
+        if (tid == 0) {
+          for (int m = 0; m < STAGES - 1 && m < my_tiles; ++m) issue_tile(m);
+        }
+        __syncwarp();
+        double R[9], t[3];
+        if (KIND == kNdt3) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) R[k] = st->R[k];
+          t[0] = st->t[0];
+          t[1] = st->t[1];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = st->R[k];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) t[k] = st->t[k];
+        }
+        for (int m = 0; m < my_tiles; ++m) {
+          const uint32_t k = ring + m;
+          const int s = k % STAGES;
+          const uint32_t phase = (k / STAGES) & 1u;
+          if (tid == 0 && m + STAGES - 1 < my_tiles) issue_tile(m + STAGES - 1);
+          __syncwarp();
+          MbarWait(&sm.full[s], phase);
+          double v[NPLANES];
+#pragma unroll
+          for (int pl = 0; pl < NPLANES; ++pl) v[pl] = sm.stages[s][pl][tid];
+          __syncwarp();
+          if (lane == 0) MbarArrive(&sm.empty[s]);
+          const int64_t idx =
+              (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
+          const bool valid = (idx >= range.begin) && (idx < range.end);
+          if (KIND == kNdt6)
+            Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+          else if (KIND == kNdt3)
+            Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+          else
+            ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
+        }
+        // warp tree (fixed order) -> shared
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          double x = acc[k];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+          acc[k] = x;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) sm.warp_sums[warp][k] = acc[k];
+        }
+      }
+      ring += my_tiles;
+      __syncthreads();
+
+      // CTA sum over the 8 consumer warps, fixed order
+      if (tid < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) s += sm.warp_sums[w][tid];
+        sm.total[tid] = s;
+      }
+      bool is_last = true;
+      if (grid_x > 1) {
+        double* my_partial = p.partials + (static_cast<size_t>(problem) * grid_x + blockIdx.x) * NACC;
+        if (tid < NACC) {
+          __stcg(my_partial + tid, sm.total[tid]);
+          __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
+          sm.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
+          if (sm.flag) p.tickets[problem] = 0u;  // ready for the next launch
+        }
+        __syncthreads();
+        is_last = sm.flag != 0;
+        if (!is_last) return;
+        __threadfence();
+        // cross-CTA sum: thread (j, lane8) adds CTAs lane8, lane8+8, ...; then 8 lanes in order
+        const int j = tid >> 3, l8 = tid & 7;
+        if (j < NACC) {
+          const double* base = p.partials + static_cast<size_t>(problem) * grid_x * NACC + j;
+          double s = 0.0;
+          for (int g = l8; g < grid_x; g += 8) s += __ldcg(base + static_cast<size_t>(g) * NACC);
+          sm.warp_sums[l8][j] = s;
+        }
+        __syncthreads();
+        if (tid < NACC) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += sm.warp_sums[w][tid];
+          sm.total[tid] = s;
+        }
+      }
+      __syncthreads();
+
+      // raw -> canonical (needs the R the sums were taken at)
+      if (tid == 0 && KIND != kNdt3) {
+        double canon[kAcc6];
+        Canonical6(sm.total, st->R, canon);
+        for (int k = 0; k < kAcc6; ++k) sm.total[k] = canon[k];
+      }
+      __syncthreads();
+      if (p.use_peer) PeerAllReduce(p.peer, sm.total, NACC);
+      if (p.mode == kModeAssemble) {
+        if (tid < NACC) p.sums[problem * 32 + tid] = sm.total[tid];
+        return;
+      }
+    } else {
+      if (tid < NACC) sm.total[tid] = p.sums[problem * 32 + tid];
+      __syncthreads();
+    }
+
+    // ---------------- damped step, one thread
+    if (tid == 0) {
+      double* trace_row = nullptr;
+      if (p.trace != nullptr)
+        trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st->iteration) *
+                                  T::kTrace;
+      if (KIND == kNdt3)
+        Step3(sm.total, st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+              trace_row);
+      else
+        Step6(sm.total, st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+              trace_row);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int KIND, int LOSS>
+static cudaError_t LaunchOne(const IterParams& p, int grid_x, int num_problems,
+                             cudaStream_t stream) {
+  dim3 grid(grid_x, num_problems);
+  gn_iteration_kernel<KIND, LOSS><<<grid, kThreads, SmemBytes<KIND>(), stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t LaunchKind(int loss, const IterParams& p, int grid_x, int num_problems,
+                              cudaStream_t stream) {
+  switch (loss) {
+    case kLossNone: return LaunchOne<KIND, kLossNone>(p, grid_x, num_problems, stream);
+    case kLossExponential: return LaunchOne<KIND, kLossExponential>(p, grid_x, num_problems, stream);
+    case kLossHuber: return LaunchOne<KIND, kLossHuber>(p, grid_x, num_problems, stream);
+    case kLossCauchy: return LaunchOne<KIND, kLossCauchy>(p, grid_x, num_problems, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
+                            cudaStream_t stream) {
+  switch (kind) {
+    case kNdt6: return LaunchKind<kNdt6>(loss, p, grid_x, num_problems, stream);
+    case kNdt3: return LaunchKind<kNdt3>(loss, p, grid_x, num_problems, stream);
+    case kReproj: return LaunchKind<kReproj>(loss, p, grid_x, num_problems, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+size_t IterationSmemBytes(int kind) {
+  switch (kind) {
+    case kNdt6: return SmemBytes<kNdt6>();
+    case kNdt3: return SmemBytes<kNdt3>();
+    default: return SmemBytes<kReproj>();
+  }
+}
+
+template <int KIND, int LOSS>
+static cudaError_t ConfigureOne() {
+  return cudaFuncSetAttribute(gn_iteration_kernel<KIND, LOSS>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(SmemBytes<KIND>()));
+}
+template <int KIND>
+static cudaError_t ConfigureKind() {
+  cudaError_t e;
+  if ((e = ConfigureOne<KIND, kLossNone>()) != cudaSuccess) return e;
+  if ((e = ConfigureOne<KIND, kLossExponential>()) != cudaSuccess) return e;
+  if ((e = ConfigureOne<KIND, kLossHuber>()) != cudaSuccess) return e;
+  return ConfigureOne<KIND, kLossCauchy>();
+}
+cudaError_t ConfigureKernels() {
+  cudaError_t e;
+  if ((e = ConfigureKind<kNdt6>()) != cudaSuccess) return e;
+  if ((e = ConfigureKind<kNdt3>()) != cudaSuccess) return e;
+  return ConfigureKind<kReproj>();
+}
+
+// ------------------------------------------------------------------ state init / finish
+__global__ void init_states_kernel(State* states, const double* poses16, int num_problems,
+                                   int kind) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_problems) return;
+  const double* P = poses16 + 16 * static_cast<size_t>(i);  // column-major 4x4
+  State s;
+  for (int k = 0; k < 9; ++k) s.R[k] = 0.0;
+  for (int k = 0; k < 4; ++k) s.q[k] = 0.0;
+  if (kind == kNdt3) {
+    // ..._analytic_3dof.cc:22-24: top-left 2x2 and xy translation, no re-orthonormalisation
+    s.t[0] = P[12]; s.t[1] = P[13]; s.t[2] = 0.0;
+    s.R[0] = P[0]; s.R[1] = P[4]; s.R[2] = P[1]; s.R[3] = P[5];
+  } else {
+    // ..._analytic.cc:86-87: Orientation(initial_pose.rotation()) then toRotationMatrix()
+    double Rin[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Rin[3 * r + c] = P[4 * c + r];
+    RotToQuat(Rin, s.q);
+    QuatToRot(s.q, s.R);
+    s.t[0] = P[12]; s.t[1] = P[13]; s.t[2] = P[14];
+  }
+  s.lambda = 0.001;
+  s.previous_cost = DBL_MAX;
+  s.iteration = 0;
+  s.done = 0;
+  s.status = 0;
+  s.pad = 0;
+  states[i] = s;
+}
+
+// results4: per problem {iterations, status, final_cost, unused}
+__global__ void finish_states_kernel(const State* states, double* poses16, double* results4,
+                                     int num_problems, int kind) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_problems) return;
+  const State& s = states[i];
+  double* P = poses16 + 16 * static_cast<size_t>(i);
+  if (kind == kNdt3) {
+    P[12] = s.t[0]; P[13] = s.t[1];
+    P[0] = s.R[0]; P[4] = s.R[1]; P[1] = s.R[2]; P[5] = s.R[3];
+  } else {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) P[4 * c + r] = s.R[3 * r + c];
+    P[12] = s.t[0]; P[13] = s.t[1]; P[14] = s.t[2];
+  }
+  results4[4 * i + 0] = static_cast<double>(s.iteration);
+  results4[4 * i + 1] = static_cast<double>(s.status);
+  results4[4 * i + 2] = s.previous_cost;
+  results4[4 * i + 3] = 0.0;
+}
+
+cudaError_t LaunchInitStates(State* states, const double* poses16, int num_problems, int kind,
+                             cudaStream_t stream) {
+  const int threads = 128;
+  init_states_kernel<<<(num_problems + threads - 1) / threads, threads, 0, stream>>>(
+      states, poses16, num_problems, kind);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchFinishStates(const State* states, double* poses16, double* results4,
+                               int num_problems, int kind, cudaStream_t stream) {
+  const int threads = 128;
+  finish_states_kernel<<<(num_problems + threads - 1) / threads, threads, 0, stream>>>(
+      states, poses16, results4, num_problems, kind);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ pack / unpack (AoS <-> planes)
+struct PlanePtrs {
+  double* p[kNdtPlanes];
+};
+
+__global__ void pack_ndt_kernel(const double* __restrict__ point, const double* __restrict__ mean,
+                                const double* __restrict__ sqrt_info, int64_t n, PlanePtrs planes,
+                                int64_t dst_offset) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t d = dst_offset + i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mean[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) planes.p[6 + k][d] = sqrt_info[9 * i + k];
+  }
+}
+
+// one CTA row per registration: source is the plain concatenation, destination is tile-aligned
+__global__ void pack_ndt_batched_kernel(const double* __restrict__ point,
+                                        const double* __restrict__ mean,
+                                        const double* __restrict__ sqrt_info,
+                                        const int64_t* __restrict__ src_prefix,
+                                        const Range* __restrict__ ranges, PlanePtrs planes) {
+  const int b = blockIdx.y;
+  const int64_t src0 = src_prefix[b];
+  const int64_t n = src_prefix[b + 1] - src0;
+  const int64_t dst0 = ranges[b].begin;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t s = src0 + i, d = dst0 + i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * s + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mean[3 * s + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) planes.p[6 + k][d] = sqrt_info[9 * s + k];
+  }
+}
+
+__global__ void pack_ndt_aos_kernel(const unsigned char* __restrict__ records, int64_t n,
+                                    size_t stride_bytes, size_t off_point, size_t off_mean,
+                                    size_t off_sqrt, int col_major, PlanePtrs planes) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned char* rec = records + static_cast<size_t>(i) * stride_bytes;
+    const double* pt = reinterpret_cast<const double*>(rec + off_point);
+    const double* mu = reinterpret_cast<const double*>(rec + off_mean);
+    const double* S = reinterpret_cast<const double*>(rec + off_sqrt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[k][i] = pt[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) planes.p[3 + k][i] = mu[k];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) planes.p[6 + 3 * r + c][i] = col_major ? S[3 * c + r] : S[3 * r + c];
+  }
+}
+
+__global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, double* point,
+                                  double* mean, double* sqrt_info) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < end;
+       i += stride) {
+    const int64_t o = i - begin;
+    for (int k = 0; k < 3; ++k) point[3 * o + k] = planes.p[k][i];
+    for (int k = 0; k < 3; ++k) mean[3 * o + k] = planes.p[3 + k][i];
+    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = planes.p[6 + k][i];
+  }
+}
+
+__global__ void pack_reproj_kernel(const double* __restrict__ local_point,
+                                   const double* __restrict__ pixel, int64_t n, PlanePtrs planes) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    planes.p[0][i] = local_point[3 * i];
+    planes.p[1][i] = local_point[3 * i + 1];
+    planes.p[2][i] = local_point[3 * i + 2];
+    planes.p[3][i] = pixel[2 * i];
+    planes.p[4][i] = pixel[2 * i + 1];
+  }
+}
+
+static int GridFor(int64_t n, int threads) {
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+static PlanePtrs MakePlanes(double* const* planes, int count) {
+  PlanePtrs pp;
+  for (int k = 0; k < kNdtPlanes; ++k) pp.p[k] = (k < count) ? planes[k] : nullptr;
+  return pp;
+}
+
+cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
+                          int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
+                          cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pack_ndt_kernel<<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
+                                                       MakePlanes(planes, kNdtPlanes), dst_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
+                                 int64_t n_total, const int64_t* src_prefix, const Range* ranges,
+                                 int num_problems, double* const planes[kNdtPlanes],
+                                 cudaStream_t stream) {
+  if (n_total <= 0) return cudaSuccess;
+  const int64_t per = (n_total + num_problems - 1) / num_problems;
+  int gx = static_cast<int>((per + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, num_problems);
+  pack_ndt_batched_kernel<<<grid, 256, 0, stream>>>(point, mean, sqrt_info, src_prefix, ranges,
+                                                    MakePlanes(planes, kNdtPlanes));
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t stride,
+                             size_t off_point, size_t off_mean, size_t off_sqrt, int col_major,
+                             double* const planes[kNdtPlanes], cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pack_ndt_aos_kernel<<<GridFor(n, 256), 256, 0, stream>>>(
+      records, n, stride, off_point, off_mean, off_sqrt, col_major, MakePlanes(planes, kNdtPlanes));
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int64_t end,
+                            double* point, double* mean, double* sqrt_info, cudaStream_t stream) {
+  if (end <= begin) return cudaSuccess;
+  unpack_ndt_kernel<<<GridFor(end - begin, 256), 256, 0, stream>>>(MakePlanes(planes, kNdtPlanes),
+                                                                  begin, end, point, mean, sqrt_info);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
+                             double* const planes[kReprojPlanes], cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pack_reproj_kernel<<<GridFor(n, 256), 256, 0, stream>>>(local_point, pixel, n,
+                                                          MakePlanes(planes, kReprojPlanes));
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ synthetic scan + dense-grid association
+__device__ __forceinline__ uint64_t SplitMix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double U01(uint64_t bits) {
+  return static_cast<double>(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Room of tests/simple_optimization_test.cc:170-204: floor 7x5 at z=0 and four walls, height 2.5.
+// Surfaces are sampled proportionally to area: floor 35, two long walls 17.5 each, two short
+// walls 12.5 each (total 95).
+__global__ void generate_ndt_kernel(const GenerateParams g) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < g.n;
+       i += stride) {
+    const uint64_t gid = static_cast<uint64_t>(g.index_offset + i);
+    double lx = 0, ly = 0, lz = 0, mean[3] = {0, 0, 0}, S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    {
+      uint64_t h = SplitMix64(g.seed ^ SplitMix64(gid));
+      const double u0 = U01(h); h = SplitMix64(h);
+      const double u1 = U01(h); h = SplitMix64(h);
+      const double u2 = U01(h); h = SplitMix64(h);
+      const double n0 = U01(h); h = SplitMix64(h);
+      const double n1 = U01(h); h = SplitMix64(h);
+      const double n2 = U01(h); h = SplitMix64(h);
+      const double n3 = U01(h);
+      double wx, wy, wz;
+      const double a = u0 * 95.0;
+      if (a < 35.0) { wx = -3.5 + 7.0 * u1; wy = -2.5 + 5.0 * u2; wz = 0.0; }
+      else if (a < 52.5) { wx = -3.5 + 7.0 * u1; wy = -2.5; wz = 2.5 * u2; }
+      else if (a < 70.0) { wx = -3.5 + 7.0 * u1; wy = 2.5; wz = 2.5 * u2; }
+      else if (a < 82.5) { wx = -3.5; wy = -2.5 + 5.0 * u1; wz = 2.5 * u2; }
+      else { wx = 3.5; wy = -2.5 + 5.0 * u1; wz = 2.5 * u2; }
+      // Box-Muller noise (3 of 4 values used)
+      const double r0 = sqrt(-2.0 * log(fmax(n0, 1e-300))), r1 = sqrt(-2.0 * log(fmax(n2, 1e-300)));
+      double s0, c0, s1, c1;
+      sincospi(2.0 * n1, &s0, &c0);
+      sincospi(2.0 * n3, &s1, &c1);
+      wx += g.noise_sigma * r0 * c0;
+      wy += g.noise_sigma * r0 * s0;
+      wz += g.noise_sigma * r1 * c1;
+      // sensor frame: l = R_true^T (w - t_true)
+      const double dx = wx - g.t_true[0], dy = wy - g.t_true[1], dz = wz - g.t_true[2];
+      lx = g.R_true[0] * dx + g.R_true[3] * dy + g.R_true[6] * dz;
+      ly = g.R_true[1] * dx + g.R_true[4] * dy + g.R_true[7] * dz;
+      lz = g.R_true[2] * dx + g.R_true[5] * dy + g.R_true[8] * dz;
+      // association under the initial pose: the cell of the voxel containing R_init l + t_init,
+      // else the nearest valid cell mean within 1.0 m (scan order z, y, x; first strict minimum)
+      const double ix = g.R_init[0] * lx + g.R_init[1] * ly + g.R_init[2] * lz + g.t_init[0];
+      const double iy = g.R_init[3] * lx + g.R_init[4] * ly + g.R_init[5] * lz + g.t_init[1];
+      const double iz = g.R_init[6] * lx + g.R_init[7] * ly + g.R_init[8] * lz + g.t_init[2];
+      const int cx = static_cast<int>(floor((ix - g.origin[0]) * g.inv_voxel));
+      const int cy = static_cast<int>(floor((iy - g.origin[1]) * g.inv_voxel));
+      const int cz = static_cast<int>(floor((iz - g.origin[2]) * g.inv_voxel));
+      int cell = -1;
+      if (cx >= 0 && cy >= 0 && cz >= 0 && cx < g.dims[0] && cy < g.dims[1] && cz < g.dims[2]) {
+        const int own = (cz * g.dims[1] + cy) * g.dims[0] + cx;
+        if (g.cell_valid[own]) cell = own;
+      }
+      if (cell < 0) {
+        double best = 1.0;
+        for (int oz = -g.reach; oz <= g.reach; ++oz)
+          for (int oy = -g.reach; oy <= g.reach; ++oy)
+            for (int ox = -g.reach; ox <= g.reach; ++ox) {
+              const int x = cx + ox, y = cy + oy, z = cz + oz;
+              if (x < 0 || y < 0 || z < 0 || x >= g.dims[0] || y >= g.dims[1] || z >= g.dims[2]) continue;
+              const int c = (z * g.dims[1] + y) * g.dims[0] + x;
+              if (!g.cell_valid[c]) continue;
+              const double ex = ix - g.cell_mean[3 * c], ey = iy - g.cell_mean[3 * c + 1],
+                           ez = iz - g.cell_mean[3 * c + 2];
+              const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+              if (d2 < best) { best = d2; cell = c; }
+            }
+      }
+      if (cell >= 0) {
+        for (int k = 0; k < 3; ++k) mean[k] = g.cell_mean[3 * cell + k];
+        for (int k = 0; k < 9; ++k) S[k] = g.cell_sqrt_info[9 * cell + k];
+      }
+    }
+    // a point that never found a valid cell keeps S = 0 and contributes exactly nothing
+    g.planes[0][i] = lx; g.planes[1][i] = ly; g.planes[2][i] = lz;
+    for (int k = 0; k < 3; ++k) g.planes[3 + k][i] = mean[k];
+    for (int k = 0; k < 9; ++k) g.planes[6 + k][i] = S[k];
+  }
+}
+
+cudaError_t LaunchGenerateNdt(const GenerateParams& p, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  generate_ndt_kernel<<<GridFor(p.n, 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace nlo

@@ -1,0 +1,262 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): per-iteration H, g, cost within 1e-6 relative; converged
+pose within 1e-6 m / 1e-6 rad at the same iteration count.  See tests/parity.py for the metric.
+"""
+import numpy as np
+import pytest
+
+from nonlinear_optimizer_for_slam_b200 import synthetic as syn
+from parity import TOL, assert_sums_close, rotation_angle
+
+pytestmark = pytest.mark.gpu
+
+LOSSES = [(0, None), (1, [1.0, 1.0]), (1, [0.7, 2.5]), (2, [1.0]), (2, [0.05]), (3, [0.5])]
+
+
+def _rand_pose(rng, nlo):
+    R = syn.random_rotation(rng)
+    t = rng.uniform(-0.5, 0.5, 3)
+    return nlo.pose_from_Rt(R, t), R, t
+
+
+@pytest.mark.parametrize("n", [1, 31, 256, 257, 5000, 70001])
+@pytest.mark.parametrize("loss", LOSSES)
+def test_ndt6_assemble_matches_oracle(ctx, nlo, oracle, n, loss):
+    rng = np.random.default_rng(100 + n)
+    point, mean, S = syn.random_ndt_records(n, seed=n)
+    pose16, R, t = _rand_pose(rng, nlo)
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.upload(point, mean, S)
+    ctx.set_loss(loss[0], loss[1])
+    H, g, c = prob.assemble6(pose16)
+    # the reference converts the pose through a quaternion first (..._analytic.cc:86-87,99)
+    Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
+    Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, Rq, t, loss[0], loss[1], long_double=True)
+    assert_sums_close(H, g, c, Hr, gr, cr)
+    prob.close()
+
+
+@pytest.mark.parametrize("n", [4, 255, 1024, 33333])
+@pytest.mark.parametrize("loss", LOSSES)
+def test_ndt3_assemble_matches_oracle(ctx, nlo, oracle, n, loss):
+    rng = np.random.default_rng(200 + n)
+    point, mean, S = syn.random_ndt_records(n, seed=1000 + n)
+    yaw = rng.uniform(-0.4, 0.4)
+    T = syn.yaw_pose([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 0.0], yaw)
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.upload(point, mean, S)
+    ctx.set_loss(loss[0], loss[1])
+    H, g, c = prob.assemble3(syn.to_pose16(T))
+    Hr, gr, cr = oracle.ndt3_assemble(point, mean, S, T[:2, :2], T[:2, 3], loss[0], loss[1],
+                                      long_double=True)
+    assert_sums_close(H, g, c, Hr, gr, cr)
+    prob.close()
+
+
+@pytest.mark.parametrize("n", [1, 630, 4097, 50000])
+@pytest.mark.parametrize("loss", [(0, None), (1, [1.0, 1.0]), (2, [0.01]), (3, [0.01])])
+def test_reproj_assemble_matches_oracle(ctx, nlo, oracle, n, loss):
+    rng = np.random.default_rng(300 + n)
+    X, px, K = syn.pnp_problem(n, seed=n)
+    X[::7, 2] = -1.0  # behind the camera: depth gate (..._analytic.cc:119-123)
+    pose16, R, t = _rand_pose(rng, nlo)
+    prob = nlo.ReprojProblem(ctx, capacity=n)
+    prob.upload(X, px, K)
+    ctx.set_loss(loss[0], loss[1])
+    H, g, c = prob.assemble(pose16)
+    Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
+    Hr, gr, cr = oracle.reproj_assemble(X, px, K, Rq, t, loss[0], loss[1], long_double=True)
+    assert_sums_close(H, g, c, Hr, gr, cr)
+    prob.close()
+
+
+def test_assemble_ranges_and_empty(ctx, nlo, oracle):
+    n = 10000
+    point, mean, S = syn.random_ndt_records(n, seed=5)
+    prob = nlo.NdtProblem(ctx, capacity=n + 100)
+    prob.upload(point, mean, S)
+    ctx.set_loss(1, [1.0, 1.0])
+    pose16 = nlo.identity_pose()
+    total = np.zeros(28)
+    for b, e in [(0, 0), (0, 1), (1, 300), (300, 4097), (4097, 9999), (9999, 10000)]:
+        H, g, c = prob.assemble6(pose16, b, e)
+        Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, np.eye(3), np.zeros(3), 1, [1.0, 1.0],
+                                          begin=b, end=e, long_double=True)
+        if e > b:
+            assert_sums_close(H, g, c, Hr, gr, cr)
+        else:
+            assert not H.any() and not g.any() and c == 0.0
+        total += np.concatenate([H, g, [c]])
+    H, g, c = prob.assemble6(pose16)
+    # linearity: shards sum to the whole (what the multi-GPU all-reduce relies on)
+    assert_sums_close(total[:21], total[21:27], total[27], H, g, c, tol=1e-12)
+    prob.close()
+
+
+def _check_trajectory(res, ref, width, nlo, three_dof=False):
+    pose_r, it_r, cost_r, trace_r = ref
+    assert res["iterations"] == it_r
+    assert res["trace"].shape == trace_r.shape
+    nh = 6 if three_dof else 21
+    ng = 3 if three_dof else 6
+    for k in range(trace_r.shape[0]):
+        a, b = res["trace"][k], trace_r[k]
+        assert_sums_close(a[:nh], a[nh:nh + ng], a[nh + ng], b[:nh], b[nh:nh + ng], b[nh + ng])
+        np.testing.assert_allclose(a[nh + ng + 1:], b[nh + ng + 1:], rtol=0, atol=1e-6)
+    Ra, ta = nlo.pose_to_Rt(res["pose"])
+    Rb, tb = nlo.pose_to_Rt(pose_r)
+    assert np.max(np.abs(ta - tb)) < 1e-6
+    assert rotation_angle(Ra, Rb) < 1e-6
+    assert abs(res["final_cost"] - cost_r) <= TOL * abs(cost_r)
+
+
+def test_pnp_known_answer(ctx, nlo, oracle):
+    """results/reproj_amd64.txt:5,10 -- COST: 2.33228e-11, iter: 6, pose^-1 = (-0.1, 0.123, -0.5)."""
+    X, px, K = syn.pnp_fixture()
+    prob = nlo.ReprojProblem(ctx, capacity=len(X))
+    prob.upload(X, px, K)
+    ctx.set_loss(1, [1.0, 1.0])
+    res = prob.solve(nlo.identity_pose(), trace=True)
+    assert res["iterations"] == 6
+    assert "%.5e" % res["final_cost"] == "2.33228e-11"
+    R, t = nlo.pose_to_Rt(res["pose"])
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+    Ti = np.linalg.inv(T)
+    np.testing.assert_allclose(Ti[:3, 3], [-0.1, 0.123, -0.5], atol=5e-7)
+    q = oracle.rotmat_to_quat(Ti[:3, :3])
+    np.testing.assert_allclose(q, [0, 0, 0.0499792, 0.99875], atol=5e-7)
+    ref = oracle.reproj_solve(X, px, K, nlo.identity_pose(), 1, [1.0, 1.0])
+    _check_trajectory(res, ref, 36, nlo)
+    prob.close()
+
+
+@pytest.mark.parametrize("n,loss", [(3000, (1, [1.0, 1.0])), (100000, (1, [1.0, 1.0])),
+                                    (20000, (0, None)), (20000, (2, [1.0]))])
+def test_ndt6_solve_trajectory(ctx, nlo, oracle, n, loss):
+    point, mean, S = syn.ndt_problem(n, 1001, syn.CFG1_TRUE)
+    prob = nlo.NdtProblem(ctx, capacity=len(point))
+    prob.upload(point, mean, S)
+    ctx.set_loss(loss[0], loss[1])
+    res = prob.solve6(nlo.identity_pose(), trace=True)
+    ref = oracle.ndt6_solve(point, mean, S, nlo.identity_pose(), loss[0], loss[1])
+    _check_trajectory(res, ref, 36, nlo)
+    prob.close()
+
+
+@pytest.mark.parametrize("n,loss", [(2001, (2, [1.0])), (200000, (2, [1.0])), (30000, (1, [1.0, 1.0]))])
+def test_ndt3_solve_trajectory(ctx, nlo, oracle, n, loss):
+    point, mean, S = syn.ndt_problem(n, 1002, syn.CFG2_TRUE)
+    prob = nlo.NdtProblem(ctx, capacity=len(point))
+    prob.upload(point, mean, S)
+    ctx.set_loss(loss[0], loss[1])
+    init = syn.to_pose16(syn.yaw_pose([0.02, -0.01, 0.3], 0.03))  # z and 3-D part must survive
+    res = prob.solve3(init, trace=True)
+    ref = oracle.ndt3_solve(point, mean, S, init, loss[0], loss[1])
+    _check_trajectory(res, ref, 17, nlo, three_dof=True)
+    np.testing.assert_array_equal(res["pose"][[2, 6, 8, 9, 10, 14]], init[[2, 6, 8, 9, 10, 14]])
+    prob.close()
+
+
+def test_reproj_solve_cauchy(ctx, nlo, oracle):
+    X, px, K = syn.pnp_problem(50000, 1003)
+    prob = nlo.ReprojProblem(ctx, capacity=len(X))
+    prob.upload(X, px, K)
+    ctx.set_loss(3, [1e-2])
+    res = prob.solve(nlo.identity_pose(), trace=True)
+    ref = oracle.reproj_solve(X, px, K, nlo.identity_pose(), 3, [1e-2])
+    _check_trajectory(res, ref, 36, nlo)
+    prob.close()
+
+
+def test_batched_matches_single(ctx, nlo, oracle):
+    rng = np.random.default_rng(7)
+    counts = [2000, 777, 5000, 256, 1]
+    pts, mus, Ss, poses, refs = [], [], [], [], []
+    ctx.set_loss(1, [1.0, 1.0])
+    for k, c in enumerate(counts):
+        T = syn.yaw_pose(rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.1, 0.1))
+        p, m, s = syn.ndt_problem(c, 2000 + k, T)
+        pts.append(p); mus.append(m); Ss.append(s)
+        poses.append(nlo.identity_pose())
+        refs.append(oracle.ndt6_solve(p, m, s, nlo.identity_pose(), 1, [1.0, 1.0]))
+    prob = nlo.NdtProblem(ctx, counts=[len(p) for p in pts])
+    prob.upload(np.concatenate(pts), np.concatenate(mus), np.concatenate(Ss))
+    out = prob.solve6_batched(np.stack(poses))
+    for k in range(len(counts)):
+        pose_r, it_r, cost_r, _ = refs[k]
+        assert out["iterations"][k] == it_r
+        Ra, ta = nlo.pose_to_Rt(out["poses"][k]); Rb, tb = nlo.pose_to_Rt(pose_r)
+        assert np.max(np.abs(ta - tb)) < 1e-6 and rotation_angle(Ra, Rb) < 1e-6
+        assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
+        H, g, c = prob.assemble6(nlo.identity_pose(), problem_index=k)
+        Hr, gr, cr = oracle.ndt6_assemble(pts[k], mus[k], Ss[k], np.eye(3), np.zeros(3), 1, [1.0, 1.0],
+                                          long_double=True)
+        assert_sums_close(H, g, c, Hr, gr, cr)
+    prob.close()
+
+
+def test_upload_aos_reference_layout(ctx, nlo, oracle):
+    """std::vector<Correspondence> layout: point(24) | NDT{count(4)+pad, sum, moment, mean,
+    information, sqrt_information (Eigen column-major), is_valid, is_planar} = 304 bytes."""
+    n = 3000
+    point, mean, S = syn.random_ndt_records(n, seed=11)
+    stride = 304
+    off_point, off_mean, off_sqrt = 0, 24 + 8 + 24 + 72, 24 + 8 + 24 + 72 + 24 + 72
+    rec = np.zeros((n, stride), dtype=np.uint8)
+    rec[:, off_point:off_point + 24] = point.view(np.uint8).reshape(n, 24)
+    rec[:, off_mean:off_mean + 24] = mean.view(np.uint8).reshape(n, 24)
+    S_col = np.ascontiguousarray(S.reshape(n, 3, 3).transpose(0, 2, 1)).reshape(n, 9)
+    rec[:, off_sqrt:off_sqrt + 72] = S_col.view(np.uint8).reshape(n, 72)
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.upload_aos(rec, n, stride, off_point, off_mean, off_sqrt, True)
+    p2, m2, s2 = prob.download(0, n)
+    np.testing.assert_array_equal(p2, point)
+    np.testing.assert_array_equal(m2, mean)
+    np.testing.assert_array_equal(s2, S)
+    prob.close()
+
+
+def test_generate_matches_host_association(ctx, nlo):
+    n = 200000
+    grid = syn.room_ndt_grid(0.5)
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    true16 = syn.to_pose16(syn.CFG1_TRUE)
+    prob.generate(n, 1004, 0, 0.01, true16, nlo.identity_pose(), grid)
+    point, mean, S = prob.download(0, n)
+    # points lie on the room surfaces (in the world frame) up to the noise
+    w = point @ syn.CFG1_TRUE[:3, :3].T + syn.CFG1_TRUE[:3, 3]
+    d = np.minimum.reduce([np.abs(w[:, 2]), np.abs(w[:, 1] + 2.5), np.abs(w[:, 1] - 2.5),
+                           np.abs(w[:, 0] + 3.5), np.abs(w[:, 0] - 3.5)])
+    assert d.max() < 0.08 and 0.004 < d.std() < 0.02
+    _, m_ref, s_ref = syn.associate_dense(point, np.eye(4), grid, keep_unmatched=True)
+    mismatch = np.any(mean != m_ref, axis=1) | np.any(S != s_ref, axis=1)
+    assert mismatch.mean() < 1e-4
+    assert (np.abs(S).sum(1) > 0).mean() > 0.99
+    # a different offset continues the same stream
+    prob2 = nlo.NdtProblem(ctx, capacity=1000)
+    prob2.generate(1000, 1004, 5000, 0.01, true16, nlo.identity_pose(), grid)
+    p2, _, _ = prob2.download(0, 1000)
+    np.testing.assert_array_equal(p2, point[5000:6000])
+    prob.close(); prob2.close()
+
+
+def test_large_generated_shards_sum_and_repeat(ctx, nlo):
+    """Size-independent properties at scale: point-range shards sum to the whole (linearity) and
+    the reduction is deterministic (bitwise repeatable)."""
+    n = 4_000_000
+    grid = syn.room_ndt_grid(0.5)
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.generate(n, 1004, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), nlo.identity_pose(), grid)
+    ctx.set_loss(1, [1.0, 1.0])
+    pose = nlo.identity_pose()
+    H, g, c = prob.assemble6(pose)
+    H2, g2, c2 = prob.assemble6(pose)
+    assert np.array_equal(H, H2) and np.array_equal(g, g2) and c == c2
+    acc = np.zeros(28)
+    cuts = [0, 1_000_003, 2_500_000, 2_500_001, n]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        Hs, gs, cs = prob.assemble6(pose, b, e)
+        acc += np.concatenate([Hs, gs, [cs]])
+    assert_sums_close(acc[:21], acc[21:27], acc[27], H, g, c, tol=1e-11)
+    prob.close()
