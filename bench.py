@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric).
+
+Workload (config.workload = "cfg4"): NDT 6-DoF registration of a 64M-point synthetic scan against
+the 0.5 m-voxel NDT map of the 7x5x2.5 m room, Exponential(1,1) loss, fp64 -- BASELINE.json
+configs[3], the configuration the metric is quoted on; it fits one B200 (7.68 GB of SoA planes).
+A "step" is one damped Gauss-Newton iteration over the whole scan: residual + analytic Jacobian +
+robust weight + reduction of the 28 H|g|cost doubles + 6x6 solve + pose update, all on the device.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            -> this repo's CUDA path
+  python bench.py --impl reference ...                           -> the reference's CPU path
+                                                                    (oracle port, all host threads)
+Under torchrun (N > 1) the scan is sharded by point range (strong scaling: 64M points in total)
+and the 28 doubles are all-reduced each iteration over NVLink (peer-memory one-shot all-reduce
+fused into the iteration kernel; --comm nccl selects ncclAllReduce instead).
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_CORR = 120  # 15 fp64 scalars: point 3 + mean 3 + sqrt_information 9
+TOTAL_POINTS = 64 * 1024 * 1024
+SEED = 1004
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per launch of the iteration kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (ts, r) in self.rows if t0 is None or (t0 - 0.05 <= ts <= t1 + 0.15)] or \
+               [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_reference_rates(sample_points, min_seconds, threads):
+    """Times the reference's CPU assembly (oracle port) on `sample_points` correspondences of the
+    same workload with all host threads: scalar double (..._analytic.cc:12-52 + executor split)
+    and float AVX2+FMA SoA (SolveFloatIntrinsicAligned, ..._simd_various.cc:1300-1447)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nlo_oracle_py as oracle
+    from nonlinear_optimizer_for_slam_b200 import synthetic as syn
+    oracle.build()
+    point, mean, S = syn.ndt_problem(sample_points, SEED, syn.CFG1_TRUE)
+    n = len(point)
+    R = np.eye(3); t = np.zeros(3)
+    planes = oracle.simd_pack(point, mean, S)
+    out = {}
+    for name, fn in (
+            ("scalar_f64", lambda: oracle.ndt6_assemble_threads(point, mean, S, R, t, 1, [1.0, 1.0], threads)),
+            ("avx2_f32", lambda: oracle.simd_ndt6_assemble(planes, n, R, t, 1, [1.0, 1.0], threads))):
+        fn()  # warm
+        passes, t0 = 0, time.perf_counter()
+        while True:
+            fn(); passes += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds and passes >= 3:
+                break
+        out[name] = {"gpoints_s": n * passes / dt / 1e9, "passes": passes, "seconds": dt}
+    return n, out
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4_000_000
+    # each "step" is one assembly pass over the bounded sample; W warm-up, K timed
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nlo_oracle_py as oracle
+    from nonlinear_optimizer_for_slam_b200 import synthetic as syn
+    oracle.build()
+    point, mean, S = syn.ndt_problem(sample, SEED, syn.CFG1_TRUE)
+    n = len(point)
+    planes = oracle.simd_pack(point, mean, S)
+    R = np.eye(3); t = np.zeros(3)
+    step = lambda: oracle.simd_ndt6_assemble(planes, n, R, t, 1, [1.0, 1.0], threads)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e9
+    # the double-precision scalar path, for the record
+    ts = time.perf_counter()
+    oracle.ndt6_assemble_threads(point, mean, S, R, t, 1, [1.0, 1.0], threads)
+    scalar = n / (time.perf_counter() - ts) / 1e9
+    sample_txt = ("%d correspondences of cfg4 (same generator, seed %d) per step, float AVX2+FMA SoA "
+                  "assembly (SolveFloatIntrinsicAligned restated) on %d std::threads" % (n, SEED, threads))
+    line = {
+        "impl": "reference", "metric": "NDT 6-DoF assembly Gpoints/s", "value": value,
+        "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 (reference SIMD path); f64 scalar path %.4f Gpoints/s" % scalar,
+        "data": "synthetic",
+        "config": {"workload": "cfg4: NDT 6-DoF, 64M-point scan vs 0.5 m-voxel NDT map, Exponential(1,1)",
+                   "sample_points": n},
+        "cpu_baseline": {"value": value, "unit": "Gpoints/s", "cores": threads, "kind": "port",
+                         "sample": sample_txt, "scalar_f64_gpoints_s": scalar},
+        "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import nonlinear_optimizer_for_slam_b200 as nlo
+    from nonlinear_optimizer_for_slam_b200 import synthetic as syn
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+
+    total = args.points
+    n_local = total // world
+    offset = rank * n_local
+    if rank == world - 1:
+        n_local = total - offset
+
+    ctx = nlo.Context(local_rank)
+    ctx.set_loss(nlo.LOSS_EXPONENTIAL, [1.0, 1.0])
+    grid = syn.room_ndt_grid(0.5)
+    prob = nlo.NdtProblem(ctx, capacity=n_local)
+    true16 = syn.to_pose16(syn.CFG1_TRUE)
+    prob.generate(n_local, SEED, offset, 0.01, true16, nlo.identity_pose(), grid)
+
+    comm = "none"
+    if world > 1:
+        comm = args.comm
+        if comm == "peer":
+            try:
+                handle = ctx.comm_peer_export()
+                handles = [None] * world
+                dist.all_gather_object(handles, handle)
+                ctx.comm_peer_init(handles, rank, world)
+            except Exception as e:  # CUDA IPC not permitted in this container -> NCCL
+                ok = 0
+                if rank == 0:
+                    print("peer comm unavailable (%s); falling back to NCCL" % e, file=sys.stderr)
+                comm = "nccl"
+            flags = [None] * world
+            dist.all_gather_object(flags, comm)
+            if any(f != "peer" for f in flags) and comm == "peer":
+                ctx.comm_destroy()
+                comm = "nccl"
+        if comm == "nccl":
+            uid = [ctx.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init_nccl(uid[0], rank, world)
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    never = dict(parameter_tolerance=0.0, gradient_tolerance=0.0)  # norm < 0 is never true
+    pose0 = nlo.identity_pose()
+    # warm-up: W untimed steps (also instantiates the CUDA graph of a K-step loop)
+    prob.solve6(pose0, nlo.Options(max_iterations=max(args.warmup, 3), **never))
+    prob.solve6(pose0, nlo.Options(max_iterations=args.steps, **never))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t0 = time.perf_counter()
+    res = prob.solve6(pose0, nlo.Options(max_iterations=args.steps, **never))
+    barrier()
+    t1 = time.perf_counter()
+    assert res["iterations"] == args.steps, res
+    ms_local = res["device_ms"]  # CUDA events on the context stream around the K-iteration loop
+    ms = ms_local
+    if dist is not None:
+        import torch
+        tms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    value = total * args.steps / (ms * 1e-3) / 1e9
+    iters_per_s = args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    achieved = n_local * BYTES_PER_CORR * args.steps / (ms_local * 1e-3) / 1e9
+
+    # ---- e2e: one reference-facing Solve from HOST buffers (upload + loop + pose read-back)
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(nlo, ctx, prob, n_local, args, dist, total)
+
+    # ---- secondary: latency-bound configs (iterations/s), N = 1 only
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra = measure_small_configs(nlo, syn, ctx)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        n_s, rates = cpu_reference_rates(2_000_000, 4.0, threads)
+        cpu = {"value": rates["avx2_f32"]["gpoints_s"], "unit": "Gpoints/s", "cores": threads,
+               "kind": "port",
+               "sample": "%d correspondences of cfg4, >= 4 s per variant; value = float AVX2+FMA SoA "
+                         "path (fastest reference variant) on all threads" % n_s,
+               "scalar_f64_gpoints_s": rates["scalar_f64"]["gpoints_s"]}
+
+    if rank == 0:
+        launches_per_step = 1 if comm != "nccl" else 2
+        line = {
+            "metric": "NDT 6-DoF assembly Gpoints/s", "value": value, "unit": "Gpoints/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gn_iterations_per_s": iters_per_s,
+            "config": {"workload": "cfg4: NDT 6-DoF, %d-point scan vs 0.5 m-voxel NDT map, "
+                                   "Exponential(1,1), sharded by point range" % total,
+                       "points_total": total, "points_per_gpu": n_local, "comm": comm,
+                       "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
+                             % (n_local * BYTES_PER_CORR / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR,
+                         "kernel": "gn_iteration_kernel<ndt6, exponential>"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    prob.close()
+    if dist is not None:
+        barrier()
+        ctx.comm_destroy()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def measure_e2e(nlo, ctx, prob, n_local, args, dist, total):
+    """Solve() as a caller of the reference API sees it: correspondences in (pinned) host memory,
+    one upload + repack, `e2e_iters` device-resident iterations, pose read back."""
+    n_e2e = min(n_local, args.e2e_points // (1 if dist is None else dist.get_world_size()))
+    iters = args.e2e_iters
+    nbytes = n_e2e * BYTES_PER_CORR
+    try:
+        arr, handle = nlo.host_alloc(nbytes)
+    except Exception as e:
+        return {"value": None, "unit": "Gpoints/s", "error": "pinned host allocation failed: %s" % e}
+    f64 = arr.view(np.float64)
+    point = f64[:3 * n_e2e]; mean = f64[3 * n_e2e:6 * n_e2e]; sq = f64[6 * n_e2e:15 * n_e2e]
+    # fill the host buffers with this rank's own correspondences (device -> host, untimed)
+    chunk = 4 * 1024 * 1024
+    for b in range(0, n_e2e, chunk):
+        e = min(n_e2e, b + chunk)
+        p, m, s = prob.download(b, e)
+        point[3 * b:3 * e] = p.ravel(); mean[3 * b:3 * e] = m.ravel(); sq[9 * b:9 * e] = s.ravel()
+    e2e_prob = nlo.NdtProblem(ctx, capacity=n_e2e)
+    opts = nlo.Options(max_iterations=iters, parameter_tolerance=0.0, gradient_tolerance=0.0)
+    pose0 = nlo.identity_pose()
+
+    def one_solve():
+        e2e_prob.upload_ptr(n_e2e, point.ctypes.data, mean.ctypes.data, sq.ctypes.data)
+        return e2e_prob.solve6(pose0, opts)
+
+    one_solve()  # warm-up (staging buffer, graph)
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = one_solve()
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / reps
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    world = 1 if dist is None else dist.get_world_size()
+    e2e_prob.close()
+    nlo.host_free(handle)
+    return {"value": n_e2e * world * iters / dt / 1e9, "unit": "Gpoints/s",
+            "h2d_bytes_per_step": nbytes / iters, "d2h_bytes_per_step": (128 + 32) / iters,
+            "h2d_bytes_per_solve": nbytes, "solve_iterations": iters, "seconds_per_solve": dt,
+            "points_per_gpu": n_e2e,
+            "note": "one step of the e2e arm = one GN iteration inside a full Solve(): pinned host "
+                    "correspondences uploaded once per Solve (as the reference's Solve receives them), "
+                    "%d iterations on the device, pose + iteration count read back" % iters}
+
+
+def measure_small_configs(nlo, syn, ctx):
+    """cfg1-cfg3 and cfg5 (scaled to fit the default run time): device-resident GN iterations/s."""
+    out = {}
+    never = dict(parameter_tolerance=0.0, gradient_tolerance=0.0)
+    pose0 = nlo.identity_pose()
+
+    def rate(fn, iters=40, reps=5):
+        fn(iters)
+        best = min(fn(iters)["device_ms"] for _ in range(reps))
+        return iters / (best * 1e-3), best / iters * 1e3
+
+    p, m, s = syn.ndt_problem(100_000, 1001, syn.CFG1_TRUE)
+    pr = nlo.NdtProblem(ctx, capacity=len(p)); pr.upload(p, m, s)
+    ctx.set_loss(nlo.LOSS_EXPONENTIAL, [1.0, 1.0])
+    r, us = rate(lambda k: pr.solve6(pose0, nlo.Options(max_iterations=k, **never)))
+    out["cfg1_ndt6_100k"] = {"gn_iterations_per_s": r, "us_per_iteration": us, "points": len(p)}
+    pr.close()
+
+    p, m, s = syn.ndt_problem(1_000_000, 1002, syn.CFG2_TRUE)
+    pr = nlo.NdtProblem(ctx, capacity=len(p)); pr.upload(p, m, s)
+    ctx.set_loss(nlo.LOSS_HUBER, [1.0])
+    r, us = rate(lambda k: pr.solve3(pose0, nlo.Options(max_iterations=k, **never)))
+    out["cfg2_ndt3_1m_huber"] = {"gn_iterations_per_s": r, "us_per_iteration": us, "points": len(p),
+                                 "gpoints_s": len(p) * r / 1e9}
+    pr.close()
+
+    X, px, K = syn.pnp_problem(50_000, 1003)
+    pr = nlo.ReprojProblem(ctx, capacity=len(X)); pr.upload(X, px, K)
+    ctx.set_loss(nlo.LOSS_CAUCHY, [1e-2])
+    r, us = rate(lambda k: pr.solve(pose0, nlo.Options(max_iterations=k, **never)))
+    out["cfg3_pnp_50k_cauchy"] = {"gn_iterations_per_s": r, "us_per_iteration": us, "points": len(X)}
+    pr.close()
+    return {"secondary": out}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--points", type=int, default=TOTAL_POINTS)
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--e2e-points", type=int, default=TOTAL_POINTS)
+    ap.add_argument("--e2e-iters", type=int, default=40)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()
