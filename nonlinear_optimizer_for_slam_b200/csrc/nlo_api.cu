@@ -75,6 +75,7 @@ constexpr size_t kPeerSlotBytes = 2 * kMaxRanks * 32 * sizeof(double);
 constexpr size_t kPeerFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
 constexpr size_t kPeerBufBytes = kPeerSlotBytes + kPeerFlagBytes;
 
+constexpr int kInCtaTiles = 3;  // a registration this small runs its whole loop inside one CTA
 constexpr int kSmallDoubles = 8192;  // pinned + device scratch for poses / sums / results
 
 }  // namespace
@@ -92,6 +93,8 @@ struct nlo_context {
   size_t staging_bytes = 0;
   double* host_small = nullptr;  // pinned
   bool use_graph = true;
+  bool use_persistent = true;
+  int grid_small = 0;  // CTAs of the persistent path for L2-resident problems
   // communicator
   int comm_kind = kCommNone;
   int rank = 0, nranks = 1;
@@ -120,6 +123,7 @@ struct nlo_problem {
   State* d_states = nullptr;  // [num_problems + 1]
   double* d_partials = nullptr;
   unsigned int* d_tickets = nullptr;  // [num_problems + 1]
+  unsigned int* d_barrier = nullptr;  // [num_problems + 1]
   double* d_sums = nullptr;           // [(num_problems + 1) * 32]
   double* d_poses = nullptr;          // [(num_problems + 1) * 16]
   double* d_results = nullptr;        // [(num_problems + 1) * 4]
@@ -206,7 +210,9 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
   NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
   NLO_CUDA_P(cudaMalloc(&pr->d_partials,
-                        static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double) * (batched ? 1 : 1)));
+                        2 * static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double)));
+  NLO_CUDA_P(cudaMalloc(&pr->d_barrier, slots * sizeof(unsigned int)));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_barrier, 0, slots * sizeof(unsigned int), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_tickets, 0, slots * sizeof(unsigned int), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
@@ -234,6 +240,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   memset(&p, 0, sizeof(p));
   for (int k = 0; k < pr->num_planes; ++k) p.planes[k] = pr->planes[k];
   p.partials = pr->d_partials;
+  p.barrier = pr->d_barrier;
   p.loss_p0 = ctx->loss_params[0];
   p.loss_p1 = ctx->loss_params[1];
   for (int k = 0; k < 6; ++k) p.intrinsics[k] = pr->intrinsics[k];
@@ -244,6 +251,10 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   p.use_peer = (ctx->comm_kind == kCommPeer) ? 1 : 0;
   p.peer = ctx->peer;
   return p;
+}
+
+bool UsePersistent(const nlo_context* ctx, const nlo_problem* pr) {
+  return ctx->use_persistent && ctx->comm_kind == kCommNone && !pr->batched;
 }
 
 int GridFor(nlo_context* ctx, int64_t begin, int64_t end) {
@@ -321,7 +332,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
   p.max_iterations = opt.max_iterations;
   const int64_t tiles = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
   const bool in_cta_loop =
-      (ctx->comm_kind == kCommNone) && (pr->batched || tiles <= 16);
+      (ctx->comm_kind == kCommNone) && (pr->batched || tiles <= kInCtaTiles);
   if (in_cta_loop) {
     // whole loop inside one CTA per registration: a single launch
     p.mode = kModeSolve;
@@ -330,6 +341,17 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     return NLO_OK;
   }
   const int grid_x = GridFor(ctx, begin_abs, end_abs);
+  if (UsePersistent(ctx, pr)) {
+    // persistent cooperative grid: the whole loop in ONE launch, one grid barrier per iteration
+    int gx = grid_x;
+    if (tiles < 4LL * ctx->grid_single) gx = static_cast<int>(std::min<int64_t>(tiles, ctx->grid_small));
+    p.mode = kModeSolve;
+    p.persistent = 1;
+    p.iterations_in_kernel = opt.max_iterations;
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, sizeof(unsigned int), ctx->stream));
+    NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream));
+    return NLO_OK;
+  }
   for (int it = 0; it < opt.max_iterations; ++it) {
     if (ctx->comm_kind == kCommNccl) {
       p.mode = kModeAssemble;
@@ -350,7 +372,9 @@ int RunLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options
             bool with_trace, int num_problems, int64_t begin_abs, int64_t end_abs) {
   // NCCL calls are left out of graph capture (their capture support depends on the library
   // build); the other paths run as one CUDA graph so the loop needs a single host call.
-  const bool graph = ctx->use_graph && ctx->comm_kind != kCommNccl;
+  const int64_t tiles_all = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
+  const bool single_launch = (ctx->comm_kind == kCommNone) && (pr->batched || tiles_all <= kInCtaTiles || UsePersistent(ctx, pr));
+  const bool graph = ctx->use_graph && ctx->comm_kind != kCommNccl && !single_launch;
   if (!graph) return EnqueueLoop(ctx, pr, kind, opt, with_trace, num_problems, begin_abs, end_abs);
   int64_t ptol_bits, gtol_bits;
   memcpy(&ptol_bits, &opt.parameter_tolerance, 8);
@@ -476,6 +500,11 @@ int nlo_context_create(int device, nlo_context** out) {
   ctx->grid_single = 2 * prop.multiProcessorCount;
   const char* env = getenv("NLO_NO_GRAPH");
   ctx->use_graph = !(env != nullptr && env[0] == '1');
+  const char* penv = getenv("NLO_NO_PERSISTENT");
+  ctx->use_persistent = !(penv != nullptr && penv[0] == '1');
+  ctx->grid_small = prop.multiProcessorCount;
+  const char* sgenv = getenv("NLO_GRID_SMALL");
+  if (sgenv != nullptr && atoi(sgenv) > 0) ctx->grid_small = atoi(sgenv);
   const char* genv = getenv("NLO_GRID");
   if (genv != nullptr && atoi(genv) > 0) ctx->grid_single = atoi(genv);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -575,6 +604,7 @@ int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
   cudaFree(pr->d_states);
   cudaFree(pr->d_partials);
   cudaFree(pr->d_tickets);
+  cudaFree(pr->d_barrier);
   cudaFree(pr->d_sums);
   cudaFree(pr->d_poses);
   cudaFree(pr->d_results);

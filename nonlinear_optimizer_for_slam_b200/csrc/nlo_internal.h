@@ -60,8 +60,9 @@ struct IterParams {
   const double* planes[kNdtPlanes];
   const Range* ranges;  // [num_problems]
   State* states;        // [num_problems]
-  double* partials;     // [num_problems][grid.x][nacc]
-  unsigned int* tickets;  // [num_problems]
+  double* partials;     // [2 parities][num_problems][grid.x][nacc]
+  unsigned int* tickets;  // [num_problems] last-CTA election of the one-iteration-per-launch path
+  unsigned int* barrier;  // [num_problems] grid barrier of the persistent path (0 at launch)
   double* sums;           // [num_problems][32] canonical H|g|cost (out for assemble, in for step-only)
   double* trace;          // nullable: [num_problems][max_iterations][trace_width]
   double loss_p0, loss_p1;
@@ -71,6 +72,7 @@ struct IterParams {
   int iterations_in_kernel;  // > 1 only when grid.x == 1 (whole loop inside one CTA)
   int mode;
   int use_peer;
+  int persistent;  // cooperative launch: the whole loop in one grid, grid barrier per iteration
   PeerComm peer;
 };
 

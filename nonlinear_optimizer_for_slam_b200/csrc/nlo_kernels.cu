@@ -94,7 +94,7 @@ struct SmemLayout {
   double stages[T::kStages][T::kPlanes][kTile];
   double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
   double total[32];            // reduced (raw, then canonical) sums
-  double pose[12];             // R (9) | t (3) broadcast for the in-CTA loop
+  State state;                 // CTA-local copy of the registration state
   uint64_t full[T::kStages];
   uint64_t empty[T::kStages];
   int flag;
@@ -102,7 +102,7 @@ struct SmemLayout {
 
 template <int KIND>
 constexpr size_t SmemBytes() {
-  return sizeof(SmemLayout<KIND>) + 128;
+  return sizeof(SmemLayout<KIND>);
 }
 
 // One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
@@ -149,6 +149,30 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
   __syncthreads();
 }
 
+// Grid-wide barrier for the persistent (cooperative-launch) path: `counter` starts at 0 for the
+// launch and only grows; barrier k completes when it reaches k * gridDim.x.  All CTAs are
+// co-resident (cudaLaunchCooperativeKernel), so spinning is safe; a 2 s timeout turns a lost CTA
+// into an error flag instead of a hang.
+__device__ __forceinline__ bool GridBarrier(unsigned int* counter, unsigned int target) {
+  __shared__ int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ok = 1;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned long long start = GlobalTimerNs();
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+      if (GlobalTimerNs() - start > 2000000000ULL) {
+        ok = 0;
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
 template <int KIND, int LOSS>
 __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
@@ -157,25 +181,26 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   constexpr int STAGES = T::kStages;
   constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(double);
 
-  extern __shared__ unsigned char smem_raw[];
-  SmemLayout<KIND>& sm = *reinterpret_cast<SmemLayout<KIND>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout<KIND>& sm = *reinterpret_cast<SmemLayout<KIND>*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int problem = blockIdx.y;
   const int grid_x = gridDim.x;
-  State* st = p.states + problem;
+  State* st_global = p.states + problem;
+  State& st = sm.state;  // CTA-local copy; in the persistent path every CTA steps it redundantly
 
-  if (p.mode != kModeStepOnly) {
-    if (tid == 0) {
+  if (tid == 0) {
+    if (p.mode != kModeStepOnly) {
       for (int s = 0; s < STAGES; ++s) {
         MbarInit(&sm.full[s], 1);
         MbarInit(&sm.empty[s], kConsumerWarps);
       }
       FenceBarrierInit();
     }
+    st = *st_global;
   }
   __syncthreads();
 
@@ -186,11 +211,15 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   const int64_t span = tile_hi - tile_lo;
   const int my_tiles =
       (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
+  const bool writer = (blockIdx.x == 0) || !p.persistent;  // who publishes state / trace / sums
 
   uint32_t ring = 0;  // tiles consumed so far by this CTA (keeps mbarrier phases across iterations)
+  // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
+  // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
+  const bool resident = (p.iterations_in_kernel > 1) && (my_tiles <= STAGES);
 
   for (int it = 0; it < p.iterations_in_kernel; ++it) {
-    if (st->done) break;  // uniform: state is only written behind a __syncthreads / launch boundary
+    if (st.done) break;  // uniform: the state only changes behind a __syncthreads
 
     if (p.mode != kModeStepOnly) {
       double acc[NACC];
@@ -211,34 +240,39 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
             BulkLoad(&sm.stages[s][pl][0], p.planes[pl] + first, kTile * sizeof(double),
                      &sm.full[s]);
         };
-        if (tid == 0) {
+        const bool need_load = !resident || it == 0;
+        if (tid == 0 && need_load) {
           for (int m = 0; m < STAGES - 1 && m < my_tiles; ++m) issue_tile(m);
         }
         __syncwarp();
         double R[9], t[3];
         if (KIND == kNdt3) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) R[k] = st->R[k];
-          t[0] = st->t[0];
-          t[1] = st->t[1];
+          for (int k = 0; k < 4; ++k) R[k] = st.R[k];
+          t[0] = st.t[0];
+          t[1] = st.t[1];
         } else {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) R[k] = st->R[k];
+          for (int k = 0; k < 9; ++k) R[k] = st.R[k];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) t[k] = st->t[k];
+          for (int k = 0; k < 3; ++k) t[k] = st.t[k];
         }
         for (int m = 0; m < my_tiles; ++m) {
           const uint32_t k = ring + m;
           const int s = k % STAGES;
           const uint32_t phase = (k / STAGES) & 1u;
-          if (tid == 0 && m + STAGES - 1 < my_tiles) issue_tile(m + STAGES - 1);
-          __syncwarp();
-          MbarWait(&sm.full[s], phase);
+          if (need_load) {
+            if (tid == 0 && m + STAGES - 1 < my_tiles) issue_tile(m + STAGES - 1);
+            __syncwarp();
+            MbarWait(&sm.full[s], phase);
+          }
           double v[NPLANES];
 #pragma unroll
           for (int pl = 0; pl < NPLANES; ++pl) v[pl] = sm.stages[s][pl][tid];
-          __syncwarp();
-          if (lane == 0) MbarArrive(&sm.empty[s]);
+          if (!resident) {
+            __syncwarp();
+            if (lane == 0) MbarArrive(&sm.empty[s]);
+          }
           const int64_t idx =
               (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
           const bool valid = (idx >= range.begin) && (idx < range.end);
@@ -262,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           for (int k = 0; k < NACC; ++k) sm.warp_sums[warp][k] = acc[k];
         }
       }
-      ring += my_tiles;
+      if (!resident) ring += my_tiles;
       __syncthreads();
 
       // CTA sum over the 8 consumer warps, fixed order
@@ -272,27 +306,36 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
         for (int w = 0; w < kConsumerWarps; ++w) s += sm.warp_sums[w][tid];
         sm.total[tid] = s;
       }
-      bool is_last = true;
       if (grid_x > 1) {
-        double* my_partial = p.partials + (static_cast<size_t>(problem) * grid_x + blockIdx.x) * NACC;
+        // per-CTA partial -> HBM/L2; double-buffered by iteration parity for the persistent path
+        double* partial_base =
+            p.partials + static_cast<size_t>((it & 1) * gridDim.y + problem) * grid_x * NACC;
         if (tid < NACC) {
-          __stcg(my_partial + tid, sm.total[tid]);
+          __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, sm.total[tid]);
           __threadfence();
         }
-        __syncthreads();
-        if (tid == 0) {
-          const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
-          sm.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
-          if (sm.flag) p.tickets[problem] = 0u;  // ready for the next launch
+        if (p.persistent) {
+          // every CTA waits for all partials, then reduces and steps redundantly (no broadcast)
+          if (!GridBarrier(p.barrier + problem, static_cast<unsigned int>(it + 1) * grid_x)) {
+            if (tid == 0) { st.status = 2; st.done = 1; if (writer) *st_global = st; }
+            __syncthreads();
+            break;
+          }
+        } else {
+          __syncthreads();
+          if (tid == 0) {
+            const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
+            sm.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
+            if (sm.flag) p.tickets[problem] = 0u;  // ready for the next launch
+          }
+          __syncthreads();
+          if (sm.flag == 0) return;  // only the last CTA to arrive carries on
+          __threadfence();
         }
-        __syncthreads();
-        is_last = sm.flag != 0;
-        if (!is_last) return;
-        __threadfence();
-        // cross-CTA sum: thread (j, lane8) adds CTAs lane8, lane8+8, ...; then 8 lanes in order
+        // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
         const int j = tid >> 3, l8 = tid & 7;
         if (j < NACC) {
-          const double* base = p.partials + static_cast<size_t>(problem) * grid_x * NACC + j;
+          const double* base = partial_base + j;
           double s = 0.0;
           for (int g = l8; g < grid_x; g += 8) s += __ldcg(base + static_cast<size_t>(g) * NACC);
           sm.warp_sums[l8][j] = s;
@@ -310,13 +353,13 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       // raw -> canonical (needs the R the sums were taken at)
       if (tid == 0 && KIND != kNdt3) {
         double canon[kAcc6];
-        Canonical6(sm.total, st->R, canon);
+        Canonical6(sm.total, st.R, canon);
         for (int k = 0; k < kAcc6; ++k) sm.total[k] = canon[k];
       }
       __syncthreads();
       if (p.use_peer) PeerAllReduce(p.peer, sm.total, NACC);
       if (p.mode == kModeAssemble) {
-        if (tid < NACC) p.sums[problem * 32 + tid] = sm.total[tid];
+        if (tid < NACC && writer) p.sums[problem * 32 + tid] = sm.total[tid];
         return;
       }
     } else {
@@ -324,18 +367,19 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       __syncthreads();
     }
 
-    // ---------------- damped step, one thread
+    // ---------------- damped step, one thread (redundantly per CTA in the persistent path)
     if (tid == 0) {
       double* trace_row = nullptr;
-      if (p.trace != nullptr)
-        trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st->iteration) *
+      if (p.trace != nullptr && writer)
+        trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st.iteration) *
                                   T::kTrace;
       if (KIND == kNdt3)
-        Step3(sm.total, st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+        Step3(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
               trace_row);
       else
-        Step6(sm.total, st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+        Step6(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
               trace_row);
+      if (writer) *st_global = st;
     }
     __syncthreads();
   }
@@ -346,6 +390,12 @@ template <int KIND, int LOSS>
 static cudaError_t LaunchOne(const IterParams& p, int grid_x, int num_problems,
                              cudaStream_t stream) {
   dim3 grid(grid_x, num_problems);
+  if (p.persistent) {
+    IterParams copy = p;
+    void* args[] = {&copy};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS>),
+                                       grid, dim3(kThreads), args, SmemBytes<KIND>(), stream);
+  }
   gn_iteration_kernel<KIND, LOSS><<<grid, kThreads, SmemBytes<KIND>(), stream>>>(p);
   return cudaGetLastError();
 }
