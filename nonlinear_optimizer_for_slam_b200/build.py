@@ -54,6 +54,25 @@ def build_cuda(force=False, verbose=False):
     return LIB_PATH
 
 
+CXX_TEST_SRC = os.path.join(_PKG, "cxx", "tests", "simple_optimization_test.cc")
+CXX_TEST_BIN = os.path.join(_PKG, "cxx", "tests", "simple_optimization_test")
+
+
+def build_cxx_example(force=False):
+    """Compile the C++ drop-in example / test against libnlo_cuda.so (g++, no CUDA headers)."""
+    build_cuda()
+    if (not force and os.path.exists(CXX_TEST_BIN)
+            and os.path.getmtime(CXX_TEST_BIN) >= os.path.getmtime(CXX_TEST_SRC)
+            and os.path.getmtime(CXX_TEST_BIN) >= os.path.getmtime(LIB_PATH)):
+        return CXX_TEST_BIN
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra",
+           "-I", os.path.join(_PKG, "..", "include"), "-I", os.path.join(_PKG, "cxx"),
+           CXX_TEST_SRC, "-o", CXX_TEST_BIN, "-L", _PKG, "-lnlo_cuda",
+           "-Wl,-rpath," + _PKG, "-Wl,-rpath,$ORIGIN/../.."]
+    subprocess.run(cmd, check=True)
+    return CXX_TEST_BIN
+
+
 if __name__ == "__main__":
     import sys
     print(build_cuda(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
