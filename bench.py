@@ -175,7 +175,7 @@ def run_reference(args):
         "impl": "reference", "metric": "NDT 6-DoF assembly Gpoints/s", "value": value,
         "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 (reference SIMD path); f64 scalar path %.4f Gpoints/s" % scalar,
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "cfg4: NDT 6-DoF, 64M-point scan vs 0.5 m-voxel NDT map, Exponential(1,1)",
                    "sample_points": n},
@@ -297,7 +297,10 @@ def run_cuda(args):
                "scalar_f64_gpoints_s": rates["scalar_f64"]["gpoints_s"]}
 
     if rank == 0:
-        launches_per_step = 1 if comm != "nccl" else 2
+        # N = 1: the whole K-iteration loop is ONE persistent cooperative launch of
+        # gn_iteration_kernel (grid barrier per iteration); peer: one launch per iteration;
+        # nccl: assemble + step kernels per iteration (plus NCCL's own kernel, not counted)
+        launches = 1 if world == 1 else (args.steps if comm == "peer" else 2 * args.steps)
         line = {
             "metric": "NDT 6-DoF assembly Gpoints/s", "value": value, "unit": "Gpoints/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -312,11 +315,12 @@ def run_cuda(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR,
+                         "algorithmic_bytes_per_iteration": n_local * BYTES_PER_CORR,
+                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR * (args.steps if world == 1 else 1),
                          "kernel": "gn_iteration_kernel<ndt6, exponential>"},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches,
             "clocks": clocks,
         }
         line.update(extra)

@@ -225,22 +225,40 @@ void BuildNdtMap(const std::vector<Vec3>& points, double voxel, NdtMap* map) {  
   }
 }
 
-// Association: the valid cell whose voxel contains pose * point (the reference uses a KD-tree
-// over cell means, :296-342, which is outside the hot path).
-std::vector<mahalanobis_distance_minimizer::Correspondence> Match(const NdtMap& map, double voxel,
+// Association as in the reference's MatchPointCloud (:296-342): for every warped point the (at
+// most) two nearest valid cell means within 1.0 m, one correspondence per hit.  The reference
+// asks a flann KD-tree; 96 cells are few enough for an exhaustive search here.
+std::vector<mahalanobis_distance_minimizer::Correspondence> Match(const NdtMap& map, double /*voxel*/,
                                                                   const std::vector<Vec3>& local,
                                                                   const Pose& pose) {
+  std::vector<const mahalanobis_distance_minimizer::NDT*> cells;
+  for (const auto& kv : map)
+    if (kv.second.ndt.is_valid) cells.push_back(&kv.second.ndt);
   std::vector<mahalanobis_distance_minimizer::Correspondence> out;
+  out.reserve(2 * local.size());
   for (const Vec3& p : local) {
     const double q[3] = {p(0), p(1), p(2)};
     double w[3];
     Apply(pose, q, w);
-    auto it = map.find(VoxelKey(w, 1.0 / voxel));
-    if (it == map.end() || !it->second.ndt.is_valid) continue;
-    mahalanobis_distance_minimizer::Correspondence c;
-    c.point = p;
-    c.ndt = it->second.ndt;
-    out.push_back(c);
+    const mahalanobis_distance_minimizer::NDT* best[2] = {nullptr, nullptr};
+    double best_d2[2] = {1.0, 1.0};  // squared radius 1.0
+    for (const auto* ndt : cells) {
+      const double dx = w[0] - ndt->mean(0), dy = w[1] - ndt->mean(1), dz = w[2] - ndt->mean(2);
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < best_d2[0]) {
+        best_d2[1] = best_d2[0]; best[1] = best[0];
+        best_d2[0] = d2; best[0] = ndt;
+      } else if (d2 < best_d2[1]) {
+        best_d2[1] = d2; best[1] = ndt;
+      }
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (best[k] == nullptr) continue;
+      mahalanobis_distance_minimizer::Correspondence c;
+      c.point = p;
+      c.ndt = *best[k];
+      out.push_back(c);
+    }
   }
   return out;
 }
