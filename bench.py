@@ -43,12 +43,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per launch of the iteration kernel from the committed ncu capture, if any."""
+def ncu_traffic_per_launch(points, iterations_in_launch):
+    """dram__bytes_read + dram__bytes_write per launch of the iteration kernel, scaled from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json: bytes per iteration at 64M
+    points; traffic is proportional to points x iterations in the launch)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            t = json.load(f)
+        return t["dram_bytes_per_iteration"] * (points / t["points"]) * iterations_in_launch
     except Exception:
         return None
 
@@ -313,7 +316,8 @@ def run_cuda(args):
                        "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
                              % (n_local * BYTES_PER_CORR / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic_per_launch(n_local, args.steps if world == 1 else 1),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_iteration": n_local * BYTES_PER_CORR,
                          "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR * (args.steps if world == 1 else 1),
