@@ -124,6 +124,14 @@ NLO_API int nlo_ndt_generate(nlo_context* ctx, nlo_problem* problem, int64_t n, 
                      const double init_pose[16], const double grid_origin[3],
                      const int32_t grid_dims[3], double voxel_size, const double* cell_mean,
                      const double* cell_sqrt_info, const uint8_t* cell_valid);
+/* Batched twin (BASELINE cfg5): registration k gets counts[k] points from stream seed + k in the
+ * sensor frame of true_poses[16*k .. 16*k+15]; all are associated under the same init_pose. */
+NLO_API int nlo_ndt_generate_batched(nlo_context* ctx, nlo_problem* problem, uint64_t seed,
+                             double noise_sigma, const double* true_poses,
+                             const double init_pose[16], const double grid_origin[3],
+                             const int32_t grid_dims[3], double voxel_size,
+                             const double* cell_mean, const double* cell_sqrt_info,
+                             const uint8_t* cell_valid);
 /* Device -> host copy of correspondences [begin, end) in the host array convention (tests). */
 NLO_API int nlo_ndt_download(nlo_context* ctx, const nlo_problem* problem, int64_t begin, int64_t end,
                      double* point, double* mean, double* sqrt_info);

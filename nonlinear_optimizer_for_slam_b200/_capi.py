@@ -45,6 +45,9 @@ _SIGNATURES = {
                                         ctypes.c_double, c_double_p, c_double_p, c_double_p,
                                         c_int32_p, ctypes.c_double, c_double_p, c_double_p,
                                         c_uint8_p]),
+    "nlo_ndt_generate_batched": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.c_double,
+                                                c_double_p, c_double_p, c_double_p, c_int32_p,
+                                                ctypes.c_double, c_double_p, c_double_p, c_uint8_p]),
     "nlo_ndt_download": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int64, c_double_p,
                                         c_double_p, c_double_p]),
     "nlo_reproj_create": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),

@@ -207,6 +207,17 @@ class NdtProblem(_Problem):
             dims.ctypes.data_as(_capi.c_int32_p), float(grid["voxel"]), _dp(mean), _dp(sq),
             valid.ctypes.data_as(_capi.c_uint8_p)))
 
+    def generate_batched(self, seed, noise_sigma, true_poses, init_pose, grid):
+        """cfg5: registration k = stream seed + k, in the sensor frame of true_poses[k]."""
+        tp = _f64(true_poses).reshape(len(self.counts), 16); ip = _f64(init_pose).reshape(16)
+        origin = _f64(grid["origin"]); dims = np.ascontiguousarray(grid["dims"], dtype=np.int32)
+        mean = _f64(grid["mean"]); sq = _f64(grid["sqrt_info"])
+        valid = np.ascontiguousarray(grid["valid"], dtype=np.uint8)
+        self.ctx._check(self._lib.nlo_ndt_generate_batched(
+            self.ctx._h, self._h, seed, noise_sigma, _dp(tp), _dp(ip), _dp(origin),
+            dims.ctypes.data_as(_capi.c_int32_p), float(grid["voxel"]), _dp(mean), _dp(sq),
+            valid.ctypes.data_as(_capi.c_uint8_p)))
+
     def download(self, begin, end):
         n = end - begin
         point = np.zeros((n, 3)); mean = np.zeros((n, 3)); sq = np.zeros((n, 9))

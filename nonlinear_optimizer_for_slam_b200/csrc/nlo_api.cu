@@ -679,13 +679,13 @@ int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void*
   return NLO_OK;
 }
 
-int nlo_ndt_generate(nlo_context* ctx, nlo_problem* pr, int64_t n, uint64_t seed, int64_t global_index_offset,
-                     double noise_sigma, const double true_pose[16], const double init_pose[16],
-                     const double grid_origin[3], const int32_t grid_dims[3], double voxel_size,
-                     const double* cell_mean, const double* cell_sqrt_info, const uint8_t* cell_valid) {
-  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
-  if (n < 0 || n > pr->counts[0]) return Fail(ctx, NLO_EINVAL, "n exceeds capacity");
-  if (!true_pose || !init_pose || !grid_origin || !grid_dims || !cell_mean || !cell_sqrt_info || !cell_valid ||
+namespace {
+int GenerateCommon(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t global_index_offset,
+                   double noise_sigma, const double* true_poses, const double init_pose[16],
+                   const double grid_origin[3], const int32_t grid_dims[3], double voxel_size,
+                   const double* cell_mean, const double* cell_sqrt_info, const uint8_t* cell_valid,
+                   int64_t n_single) {
+  if (!true_poses || !init_pose || !grid_origin || !grid_dims || !cell_mean || !cell_sqrt_info || !cell_valid ||
       !(voxel_size > 0.0))
     return Fail(ctx, NLO_EINVAL, "null / bad grid argument");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -701,12 +701,7 @@ int nlo_ndt_generate(nlo_context* ctx, nlo_problem* pr, int64_t n, uint64_t seed
   NLO_CUDA(ctx, cudaMemcpyAsync(d_valid, cell_valid, cells, cudaMemcpyHostToDevice, ctx->stream));
   GenerateParams g;
   memset(&g, 0, sizeof(g));
-  for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k];
-  g.n = n;
-  g.seed = seed;
-  g.index_offset = global_index_offset;
   g.noise_sigma = noise_sigma;
-  PoseToRt(true_pose, g.R_true, g.t_true);
   PoseToRt(init_pose, g.R_init, g.t_init);
   for (int k = 0; k < 3; ++k) {
     g.origin[k] = grid_origin[k];
@@ -717,11 +712,43 @@ int nlo_ndt_generate(nlo_context* ctx, nlo_problem* pr, int64_t n, uint64_t seed
   g.cell_mean = d_mean;
   g.cell_sqrt_info = d_sqrt;
   g.cell_valid = d_valid;
-  NLO_CUDA(ctx, LaunchGenerateNdt(g, ctx->stream));
-  pr->n = n;
-  pr->h_ranges[0] = Range{0, n};
+  const int B = pr->batched ? pr->num_problems : 1;
+  int64_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t begin = pr->batched ? pr->h_ranges[b].begin : 0;
+    const int64_t n = pr->batched ? pr->counts[b] : n_single;
+    for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k] + begin;
+    g.n = n;
+    g.seed = seed + static_cast<uint64_t>(b);
+    g.index_offset = pr->batched ? 0 : global_index_offset;
+    PoseToRt(true_poses + 16 * static_cast<size_t>(b), g.R_true, g.t_true);
+    NLO_CUDA(ctx, LaunchGenerateNdt(g, ctx->stream));
+    total += n;
+  }
+  pr->n = total;
+  if (!pr->batched) pr->h_ranges[0] = Range{0, n_single};
   NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NLO_OK;
+}
+}  // namespace
+
+int nlo_ndt_generate(nlo_context* ctx, nlo_problem* pr, int64_t n, uint64_t seed, int64_t global_index_offset,
+                     double noise_sigma, const double true_pose[16], const double init_pose[16],
+                     const double grid_origin[3], const int32_t grid_dims[3], double voxel_size,
+                     const double* cell_mean, const double* cell_sqrt_info, const uint8_t* cell_valid) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (n < 0 || n > pr->counts[0]) return Fail(ctx, NLO_EINVAL, "n exceeds capacity");
+  return GenerateCommon(ctx, pr, seed, global_index_offset, noise_sigma, true_pose, init_pose, grid_origin,
+                        grid_dims, voxel_size, cell_mean, cell_sqrt_info, cell_valid, n);
+}
+
+int nlo_ndt_generate_batched(nlo_context* ctx, nlo_problem* pr, uint64_t seed, double noise_sigma,
+                             const double* true_poses, const double init_pose[16], const double grid_origin[3],
+                             const int32_t grid_dims[3], double voxel_size, const double* cell_mean,
+                             const double* cell_sqrt_info, const uint8_t* cell_valid) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || !pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  return GenerateCommon(ctx, pr, seed, 0, noise_sigma, true_poses, init_pose, grid_origin, grid_dims,
+                        voxel_size, cell_mean, cell_sqrt_info, cell_valid, 0);
 }
 
 int nlo_ndt_download(nlo_context* ctx, const nlo_problem* pr, int64_t begin, int64_t end, double* point,

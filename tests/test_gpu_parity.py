@@ -260,3 +260,28 @@ def test_large_generated_shards_sum_and_repeat(ctx, nlo):
         acc += np.concatenate([Hs, gs, [cs]])
     assert_sums_close(acc[:21], acc[21:27], acc[27], H, g, c, tol=1e-11)
     prob.close()
+
+
+def test_batched_generate_matches_single_generate(ctx, nlo, oracle):
+    """cfg5 generator: registration k of a batched problem = a single problem generated from
+    stream seed + k with the same true pose; the batched solve equals the oracle on those points."""
+    grid = syn.room_ndt_grid(0.5)
+    rng = np.random.default_rng(3)
+    counts = [20000, 3000, 511]
+    true = np.stack([syn.to_pose16(syn.yaw_pose(rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.15, 0.15)))
+                     for _ in counts])
+    ctx.set_loss(1, [1.0, 1.0])
+    prob = nlo.NdtProblem(ctx, counts=counts)
+    prob.generate_batched(2000, 0.01, true, nlo.identity_pose(), grid)
+    out = prob.solve6_batched(np.tile(nlo.identity_pose(), (len(counts), 1)))
+    for k, c in enumerate(counts):
+        single = nlo.NdtProblem(ctx, capacity=c)
+        single.generate(c, 2000 + k, 0, 0.01, true[k], nlo.identity_pose(), grid)
+        p, m, s = single.download(0, c)
+        pose_r, it_r, cost_r, _ = oracle.ndt6_solve(p, m, s, nlo.identity_pose(), 1, [1.0, 1.0])
+        assert out["iterations"][k] == it_r
+        Ra, ta = nlo.pose_to_Rt(out["poses"][k]); Rb, tb = nlo.pose_to_Rt(pose_r)
+        assert np.max(np.abs(ta - tb)) < 1e-6 and rotation_angle(Ra, Rb) < 1e-6
+        assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
+        single.close()
+    prob.close()
