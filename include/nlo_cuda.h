@@ -183,6 +183,64 @@ NLO_API int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* problem,
                            const nlo_solve_options* options, double* poses,
                            nlo_solve_result* results);
 
+/* ---- next rows of the scope table: device NDT map, matcher and the outer registration loop ----
+ * (the reference keeps these in its test mains, mahalanobis_distance_minimizer/tests/
+ *  simple_optimization_test.cc; they are inside every timing it publishes) */
+typedef struct nlo_ndt_map nlo_ndt_map;
+typedef struct nlo_scan nlo_scan;
+
+/* A dense-voxel-grid NDT map from host tables: cell (x,y,z) at (z*dims[1]+y)*dims[0]+x covers
+ * [origin + idx*voxel, +voxel); cell_mean[3*cells], cell_sqrt_info[9*cells] row-major,
+ * cell_valid[cells]. */
+NLO_API int nlo_ndt_map_create(nlo_context* ctx, const double grid_origin[3], const int32_t grid_dims[3],
+                       double voxel_size, const double* cell_mean, const double* cell_sqrt_info,
+                       const uint8_t* cell_valid, nlo_ndt_map** map);
+/* UpdateNdtMap (:236-280) on the device from n host points (xyz interleaved): per-voxel
+ * count/sum/moment, count >= 5, cov = (I + sum p p^T)/n - mean mean^T, symmetric 3x3
+ * eigen-decomposition, reject lambda_max < 0.01, clamp the two small eigenvalues to
+ * 0.01 lambda_max, sqrt_information = diag(lambda^-1/2) V^T -- or diag * V, exactly as the
+ * reference writes it (:275-276), when v_not_transposed != 0 (that form depends on the arbitrary
+ * eigenvector signs; here each eigenvector's largest component is made positive). */
+NLO_API int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size,
+                      int v_not_transposed, nlo_ndt_map** map);
+/* dims/origin/voxel/cells of a map; then the tables (arrays sized from the first call). */
+NLO_API int nlo_ndt_map_info(nlo_context* ctx, const nlo_ndt_map* map, double grid_origin[3],
+                     int32_t grid_dims[3], double* voxel_size, int64_t* valid_cells);
+NLO_API int nlo_ndt_map_download(nlo_context* ctx, const nlo_ndt_map* map, double* cell_mean,
+                         double* cell_sqrt_info, uint8_t* cell_valid);
+NLO_API int nlo_ndt_map_destroy(nlo_context* ctx, nlo_ndt_map* map);
+
+/* A scan (points in the sensor frame) resident on the device. */
+NLO_API int nlo_scan_create(nlo_context* ctx, int64_t n, const double* points_xyz, nlo_scan** scan);
+NLO_API int nlo_scan_destroy(nlo_context* ctx, nlo_scan* scan);
+
+/* MatchPointCloud (:296-342): for every scan point warped by `pose`, the <= max_neighbors (1 or 2)
+ * nearest valid cell means with squared distance < radius^2; fills `problem` (an nlo_ndt_create'd
+ * problem of capacity >= max_neighbors * n) with max_neighbors * n correspondences -- neighbour
+ * slot j of point i at index j*n + i, missing neighbours as zero-information records (they add
+ * exactly nothing).  *matched (nullable) = number of real correspondences. */
+NLO_API int nlo_ndt_match(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map, const double pose[16],
+                  double radius, int32_t max_neighbors, nlo_problem* problem, int64_t* matched);
+
+typedef struct nlo_register_result {
+  int32_t outer_iterations;  /* match + solve rounds executed */
+  int32_t inner_iterations;  /* sum of the solves' `iterations` */
+  int32_t status;
+  int32_t reserved;
+  double final_cost;         /* of the last solve that iterated */
+  double device_ms;          /* CUDA-event time of all match + solve work */
+  int64_t matched;           /* correspondences of the last match */
+} nlo_register_result;
+
+/* The outer loop of OptimizePoseAnalytic (:473-505): up to max_outer x { match at the current
+ * pose, Solve }, stopping when |dt| < 1e-5 and |dq.vec| < 1e-5 between rounds (:495-499).
+ * three_dof != 0 uses the planar solver (3dof_6dof_comparison_test.cc).  Everything runs on the
+ * device; the host sees one pose per round. */
+NLO_API int nlo_ndt_register(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map,
+                     const nlo_solve_options* options, double radius, int32_t max_neighbors,
+                     int32_t max_outer, int32_t three_dof, double pose[16],
+                     nlo_register_result* result);
+
 /* ---- multi-GPU (one process per GPU; a large scan sharded by point range) ----
  * With a communicator attached, every assemble/solve on the context sums its 28 (10 for 3-DoF)
  * partial doubles over all ranks each iteration and every rank applies the identical update.

@@ -18,13 +18,20 @@ class SolveOptions(ctypes.Structure):
                 ("parameter_tolerance", ctypes.c_double), ("gradient_tolerance", ctypes.c_double)]
 
 
+class RegisterResult(ctypes.Structure):
+    _fields_ = [("outer_iterations", ctypes.c_int32), ("inner_iterations", ctypes.c_int32),
+                ("status", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("final_cost", ctypes.c_double), ("device_ms", ctypes.c_double),
+                ("matched", ctypes.c_int64)]
+
+
 class SolveResult(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32),
                 ("final_cost", ctypes.c_double), ("device_ms", ctypes.c_double)]
 
 
-# name -> (restype, argtypes); every symbol include/nlo_cuda.h declares
 _VP = ctypes.c_void_p
+# name -> (restype, argtypes); every symbol include/nlo_cuda.h declares
 _SIGNATURES = {
     "nlo_abi_version": (ctypes.c_int, []),
     "nlo_context_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_VP)]),
@@ -68,6 +75,20 @@ _SIGNATURES = {
                                         ctypes.POINTER(SolveResult), c_double_p]),
     "nlo_ndt6_solve_batched": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(SolveOptions), c_double_p,
                                               ctypes.POINTER(SolveResult)]),
+    "nlo_ndt_map_create": (ctypes.c_int, [_VP, c_double_p, c_int32_p, ctypes.c_double, c_double_p,
+                                          c_double_p, c_uint8_p, ctypes.POINTER(_VP)]),
+    "nlo_ndt_map_build": (ctypes.c_int, [_VP, ctypes.c_int64, _VP, ctypes.c_double, ctypes.c_int,
+                                         ctypes.POINTER(_VP)]),
+    "nlo_ndt_map_info": (ctypes.c_int, [_VP, _VP, c_double_p, c_int32_p, c_double_p, c_int64_p]),
+    "nlo_ndt_map_download": (ctypes.c_int, [_VP, _VP, c_double_p, c_double_p, c_uint8_p]),
+    "nlo_ndt_map_destroy": (ctypes.c_int, [_VP, _VP]),
+    "nlo_scan_create": (ctypes.c_int, [_VP, ctypes.c_int64, _VP, ctypes.POINTER(_VP)]),
+    "nlo_scan_destroy": (ctypes.c_int, [_VP, _VP]),
+    "nlo_ndt_match": (ctypes.c_int, [_VP, _VP, _VP, c_double_p, ctypes.c_double, ctypes.c_int32,
+                                     _VP, c_int64_p]),
+    "nlo_ndt_register": (ctypes.c_int, [_VP, _VP, _VP, ctypes.POINTER(SolveOptions),
+                                        ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_int32, c_double_p, ctypes.POINTER(RegisterResult)]),
     "nlo_comm_unique_id": (ctypes.c_int, [_VP, c_uint8_p]),
     "nlo_comm_init_nccl": (ctypes.c_int, [_VP, c_uint8_p, ctypes.c_int32, ctypes.c_int32]),
     "nlo_comm_peer_export": (ctypes.c_int, [_VP, c_uint8_p]),

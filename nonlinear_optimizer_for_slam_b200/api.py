@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._capi import SolveOptions, SolveResult, c_double_p
+from ._capi import RegisterResult, SolveOptions, SolveResult, c_double_p
 
 LOSS_NONE, LOSS_EXPONENTIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2, 3
 TRACE6, TRACE3 = 36, 17
@@ -281,6 +281,97 @@ class ReprojProblem(_Problem):
     def solve(self, pose16, options=None, trace=False):
         """ReprojectionErrorMinimizerAnalytic::Solve, ..._analytic.cc:12-105."""
         return self._solve(self._lib.nlo_reproj_solve, TRACE6, pose16, options or Options(), trace)
+
+
+class NdtMap:
+    """Dense-voxel-grid NDT map on the device (UpdateNdtMap of the reference's test mains,
+    mahalanobis_distance_minimizer/tests/simple_optimization_test.cc:236-280)."""
+
+    def __init__(self, ctx, grid=None, points=None, voxel=None, v_not_transposed=False):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = ctypes.c_void_p()
+        if grid is not None:
+            origin = _f64(grid["origin"]); dims = np.ascontiguousarray(grid["dims"], dtype=np.int32)
+            mean = _f64(grid["mean"]); sq = _f64(grid["sqrt_info"])
+            valid = np.ascontiguousarray(grid["valid"], dtype=np.uint8)
+            ctx._check(self._lib.nlo_ndt_map_create(
+                ctx._h, _dp(origin), dims.ctypes.data_as(_capi.c_int32_p), float(grid["voxel"]),
+                _dp(mean), _dp(sq), valid.ctypes.data_as(_capi.c_uint8_p), ctypes.byref(self._h)))
+        else:
+            pts = _f64(points)
+            ctx._check(self._lib.nlo_ndt_map_build(ctx._h, pts.size // 3, pts.ctypes.data,
+                                                   float(voxel), int(v_not_transposed),
+                                                   ctypes.byref(self._h)))
+
+    def to_grid(self):
+        origin = np.zeros(3); dims = np.zeros(3, dtype=np.int32)
+        voxel = ctypes.c_double(0); nvalid = ctypes.c_int64(0)
+        self.ctx._check(self._lib.nlo_ndt_map_info(self.ctx._h, self._h, _dp(origin),
+                                                   dims.ctypes.data_as(_capi.c_int32_p),
+                                                   ctypes.byref(voxel), ctypes.byref(nvalid)))
+        cells = int(dims.astype(np.int64).prod())
+        mean = np.zeros((cells, 3)); sq = np.zeros((cells, 9)); valid = np.zeros(cells, dtype=np.uint8)
+        self.ctx._check(self._lib.nlo_ndt_map_download(self.ctx._h, self._h, _dp(mean), _dp(sq),
+                                                       valid.ctypes.data_as(_capi.c_uint8_p)))
+        return {"origin": origin, "dims": dims, "voxel": voxel.value, "mean": mean,
+                "sqrt_info": sq, "valid": valid, "valid_cells": nvalid.value}
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self._lib.nlo_ndt_map_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scan:
+    """Scan points (sensor frame) resident on the device."""
+
+    def __init__(self, ctx, points):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = ctypes.c_void_p()
+        pts = _f64(points)
+        self.n = pts.size // 3
+        ctx._check(self._lib.nlo_scan_create(ctx._h, self.n, pts.ctypes.data, ctypes.byref(self._h)))
+
+    def match(self, ndt_map, pose16, problem, radius=1.0, max_neighbors=2):
+        """MatchPointCloud (simple_optimization_test.cc:296-342) into `problem`."""
+        pose = _f64(pose16).reshape(16)
+        matched = ctypes.c_int64(0)
+        self.ctx._check(self._lib.nlo_ndt_match(self.ctx._h, self._h, ndt_map._h, _dp(pose), radius,
+                                                max_neighbors, problem._h, ctypes.byref(matched)))
+        return matched.value
+
+    def register(self, ndt_map, pose16, options=None, radius=1.0, max_neighbors=2, max_outer=10,
+                 three_dof=False):
+        """The outer match + Solve loop of OptimizePoseAnalytic (:473-505), on the device."""
+        options = options or Options()
+        pose = _f64(pose16).reshape(16).copy()
+        opt = options._c()
+        res = RegisterResult()
+        self.ctx._check(self._lib.nlo_ndt_register(self.ctx._h, self._h, ndt_map._h, ctypes.byref(opt),
+                                                   radius, max_neighbors, max_outer, int(three_dof),
+                                                   _dp(pose), ctypes.byref(res)))
+        return {"pose": pose, "outer_iterations": res.outer_iterations,
+                "inner_iterations": res.inner_iterations, "final_cost": res.final_cost,
+                "device_ms": res.device_ms, "matched": res.matched}
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self._lib.nlo_scan_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def host_alloc(nbytes):

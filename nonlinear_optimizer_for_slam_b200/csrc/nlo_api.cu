@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <array>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -132,6 +133,25 @@ struct nlo_problem {
   double intrinsics[6] = {0, 0, 0, 0, 0, 0};
   int grid_x = 1;
   std::map<std::array<int64_t, 10>, cudaGraphExec_t> graphs;
+};
+
+struct nlo_ndt_map {
+  double origin[3] = {0, 0, 0};
+  int dims[3] = {0, 0, 0};
+  double voxel = 0.0;
+  int64_t cells = 0;
+  double* d_mean = nullptr;          // [cells][3]
+  double* d_sqrt_info = nullptr;     // [cells][9] row-major
+  unsigned char* d_valid = nullptr;  // [cells]
+};
+
+struct nlo_scan {
+  int64_t n = 0;
+  double* block = nullptr;
+  double* planes[3] = {nullptr, nullptr, nullptr};
+  nlo_problem* workspace = nullptr;  // correspondences of nlo_ndt_register, grown on demand
+  int64_t workspace_capacity = 0;
+  unsigned long long* d_matched = nullptr;
 };
 
 namespace {
@@ -824,6 +844,310 @@ int nlo_reproj_solve(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options*
 int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double* poses,
                            nlo_solve_result* results) {
   return Solve(ctx, pr, kNdt6, options, poses, results, nullptr, true);
+}
+
+// ---- NDT map / scan / matcher / outer registration loop ----
+namespace {
+
+int AllocMap(nlo_context* ctx, const double origin[3], const int32_t dims[3], double voxel, nlo_ndt_map** out) {
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || !(voxel > 0.0)) return Fail(ctx, NLO_EINVAL, "bad grid");
+  const int64_t cells = static_cast<int64_t>(dims[0]) * dims[1] * dims[2];
+  if (cells > (1LL << 28)) return Fail(ctx, NLO_EINVAL, "dense grid too large (> 2^28 cells)");
+  nlo_ndt_map* m = new nlo_ndt_map();
+  for (int k = 0; k < 3; ++k) { m->origin[k] = origin[k]; m->dims[k] = dims[k]; }
+  m->voxel = voxel;
+  m->cells = cells;
+  if (cudaMalloc(&m->d_mean, cells * 3 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&m->d_sqrt_info, cells * 9 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&m->d_valid, cells) != cudaSuccess) {
+    nlo_ndt_map_destroy(ctx, m);
+    return Fail(ctx, NLO_ENOMEM, "cudaMalloc(map) failed");
+  }
+  *out = m;
+  return NLO_OK;
+}
+
+int MatchInto(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map, const double pose[16], double radius,
+              int max_neighbors, nlo_problem* pr, unsigned long long* d_matched) {
+  MatchParams mp;
+  memset(&mp, 0, sizeof(mp));
+  for (int k = 0; k < 3; ++k) mp.scan[k] = scan->planes[k];
+  mp.n = scan->n;
+  for (int k = 0; k < kNdtPlanes; ++k) mp.planes[k] = pr->planes[k];
+  PoseToRt(pose, mp.R, mp.t);
+  for (int k = 0; k < 3; ++k) { mp.origin[k] = map->origin[k]; mp.dims[k] = map->dims[k]; }
+  mp.inv_voxel = 1.0 / map->voxel;
+  mp.reach = static_cast<int>(std::ceil(radius / map->voxel));
+  mp.radius2 = radius * radius;
+  mp.max_neighbors = max_neighbors;
+  mp.cell_mean = map->d_mean;
+  mp.cell_sqrt_info = map->d_sqrt_info;
+  mp.cell_valid = map->d_valid;
+  mp.matched = d_matched;
+  if (d_matched) NLO_CUDA(ctx, cudaMemsetAsync(d_matched, 0, sizeof(unsigned long long), ctx->stream));
+  NLO_CUDA(ctx, LaunchMatchNdt(mp, ctx->stream));
+  pr->n = static_cast<int64_t>(max_neighbors) * scan->n;
+  pr->h_ranges[0] = Range{0, pr->n};
+  return NLO_OK;
+}
+
+// Eigen::Quaterniond(Matrix3d) restated on the host for the outer-loop convergence test
+void HostRotToQuat(const double* R, double* q) {
+  double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) {
+    double s = std::sqrt(tr + 1.0);
+    q[3] = 0.5 * s; s = 0.5 / s;
+    q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double s = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * s; s = 0.5 / s;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * s;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+  }
+}
+
+}  // namespace
+
+int nlo_ndt_map_create(nlo_context* ctx, const double grid_origin[3], const int32_t grid_dims[3], double voxel_size,
+                       const double* cell_mean, const double* cell_sqrt_info, const uint8_t* cell_valid,
+                       nlo_ndt_map** map) {
+  if (ctx == nullptr || map == nullptr || !grid_origin || !grid_dims || !cell_mean || !cell_sqrt_info || !cell_valid)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  nlo_ndt_map* m = nullptr;
+  int rc = AllocMap(ctx, grid_origin, grid_dims, voxel_size, &m);
+  if (rc != NLO_OK) return rc;
+  cudaError_t e = cudaMemcpyAsync(m->d_mean, cell_mean, m->cells * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_sqrt_info, cell_sqrt_info, m->cells * 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_valid, cell_valid, m->cells, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    nlo_ndt_map_destroy(ctx, m);
+    return Fail(ctx, NLO_ECUDA, std::string("map upload: ") + cudaGetErrorString(e));
+  }
+  *map = m;
+  return NLO_OK;
+}
+
+int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size, int v_not_transposed,
+                      nlo_ndt_map** map) {
+  if (ctx == nullptr || map == nullptr || points_xyz == nullptr || n <= 0 || !(voxel_size > 0.0))
+    return Fail(ctx, NLO_EINVAL, "bad argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t pbytes = static_cast<size_t>(n) * 3 * sizeof(double);
+  int rc = EnsureStaging(ctx, pbytes + 256);
+  if (rc != NLO_OK) return rc;
+  double* d_xyz = static_cast<double*>(ctx->staging);
+  int* d_bounds = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ctx->staging) + ((pbytes + 63) / 64) * 64);
+  NLO_CUDA(ctx, cudaMemcpyAsync(d_xyz, points_xyz, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+  int* hb = reinterpret_cast<int*>(ctx->host_small);
+  for (int k = 0; k < 3; ++k) { hb[k] = INT_MAX; hb[3 + k] = INT_MIN; }
+  NLO_CUDA(ctx, cudaMemcpyAsync(d_bounds, hb, 6 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  const double inv = 1.0 / voxel_size;
+  NLO_CUDA(ctx, LaunchMapBounds(d_xyz, n, inv, d_bounds, ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpyAsync(hb, d_bounds, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int32_t dims[3];
+  double origin[3];
+  int kmin[3];
+  for (int k = 0; k < 3; ++k) {
+    kmin[k] = hb[k];
+    dims[k] = hb[3 + k] - hb[k] + 1;
+    origin[k] = hb[k] * voxel_size;
+  }
+  nlo_ndt_map* m = nullptr;
+  rc = AllocMap(ctx, origin, dims, voxel_size, &m);
+  if (rc != NLO_OK) return rc;
+  int* d_count = nullptr;
+  double* d_sums = nullptr;
+  auto cleanup = [&]() { cudaFree(d_count); cudaFree(d_sums); };
+  cudaError_t e = cudaMalloc(&d_count, m->cells * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&d_sums, m->cells * 9 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, m->cells * sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, m->cells * 9 * sizeof(double), ctx->stream);
+  if (e == cudaSuccess) {
+    MapAccumParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.xyz = d_xyz; ap.n = n; ap.inv_voxel = inv;
+    for (int k = 0; k < 3; ++k) { ap.kmin[k] = kmin[k]; ap.dims[k] = dims[k]; }
+    ap.count = d_count; ap.sums = d_sums;
+    e = LaunchMapAccumulate(ap, ctx->stream);
+  }
+  if (e == cudaSuccess)
+    e = LaunchMapFinalize(d_count, d_sums, m->cells, v_not_transposed, m->d_mean, m->d_sqrt_info, m->d_valid, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess) {
+    nlo_ndt_map_destroy(ctx, m);
+    return Fail(ctx, NLO_ECUDA, std::string("map build: ") + cudaGetErrorString(e));
+  }
+  *map = m;
+  return NLO_OK;
+}
+
+int nlo_ndt_map_info(nlo_context* ctx, const nlo_ndt_map* map, double grid_origin[3], int32_t grid_dims[3],
+                     double* voxel_size, int64_t* valid_cells) {
+  if (ctx == nullptr || map == nullptr) return Fail(ctx, NLO_EINVAL, "null argument");
+  for (int k = 0; k < 3; ++k) {
+    if (grid_origin) grid_origin[k] = map->origin[k];
+    if (grid_dims) grid_dims[k] = map->dims[k];
+  }
+  if (voxel_size) *voxel_size = map->voxel;
+  if (valid_cells) {
+    NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<unsigned char> v(map->cells);
+    NLO_CUDA(ctx, cudaMemcpy(v.data(), map->d_valid, map->cells, cudaMemcpyDeviceToHost));
+    int64_t c = 0;
+    for (unsigned char x : v) c += x ? 1 : 0;
+    *valid_cells = c;
+  }
+  return NLO_OK;
+}
+
+int nlo_ndt_map_download(nlo_context* ctx, const nlo_ndt_map* map, double* cell_mean, double* cell_sqrt_info,
+                         uint8_t* cell_valid) {
+  if (ctx == nullptr || map == nullptr || !cell_mean || !cell_sqrt_info || !cell_valid)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpy(cell_mean, map->d_mean, map->cells * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  NLO_CUDA(ctx, cudaMemcpy(cell_sqrt_info, map->d_sqrt_info, map->cells * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  NLO_CUDA(ctx, cudaMemcpy(cell_valid, map->d_valid, map->cells, cudaMemcpyDeviceToHost));
+  return NLO_OK;
+}
+
+int nlo_ndt_map_destroy(nlo_context* ctx, nlo_ndt_map* map) {
+  if (map == nullptr) return NLO_OK;
+  if (ctx != nullptr) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  cudaFree(map->d_mean);
+  cudaFree(map->d_sqrt_info);
+  cudaFree(map->d_valid);
+  delete map;
+  return NLO_OK;
+}
+
+int nlo_scan_create(nlo_context* ctx, int64_t n, const double* points_xyz, nlo_scan** scan) {
+  if (ctx == nullptr || scan == nullptr || n < 0 || (n > 0 && points_xyz == nullptr)) return Fail(ctx, NLO_EINVAL, "bad argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  nlo_scan* sc = new nlo_scan();
+  sc->n = n;
+  const int64_t cap = std::max<int64_t>(n, 1);
+  if (cudaMalloc(&sc->block, cap * 3 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&sc->d_matched, sizeof(unsigned long long)) != cudaSuccess) {
+    nlo_scan_destroy(ctx, sc);
+    return Fail(ctx, NLO_ENOMEM, "cudaMalloc(scan) failed");
+  }
+  for (int k = 0; k < 3; ++k) sc->planes[k] = sc->block + static_cast<size_t>(k) * cap;
+  if (n > 0) {
+    int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 3 * sizeof(double));
+    if (rc != NLO_OK) { nlo_scan_destroy(ctx, sc); return rc; }
+    cudaError_t e = cudaMemcpyAsync(ctx->staging, points_xyz, static_cast<size_t>(n) * 3 * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = LaunchPackScan(static_cast<const double*>(ctx->staging), n, sc->planes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      nlo_scan_destroy(ctx, sc);
+      return Fail(ctx, NLO_ECUDA, std::string("scan upload: ") + cudaGetErrorString(e));
+    }
+  }
+  *scan = sc;
+  return NLO_OK;
+}
+
+int nlo_scan_destroy(nlo_context* ctx, nlo_scan* scan) {
+  if (scan == nullptr) return NLO_OK;
+  if (ctx != nullptr) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (scan->workspace) nlo_problem_destroy(ctx, scan->workspace);
+  cudaFree(scan->block);
+  cudaFree(scan->d_matched);
+  delete scan;
+  return NLO_OK;
+}
+
+int nlo_ndt_match(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map, const double pose[16], double radius,
+                  int32_t max_neighbors, nlo_problem* pr, int64_t* matched) {
+  if (ctx == nullptr || scan == nullptr || map == nullptr || pose == nullptr || pr == nullptr)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  if (pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "problem must be a single NDT problem");
+  if (max_neighbors < 1 || max_neighbors > 2 || !(radius > 0.0)) return Fail(ctx, NLO_EINVAL, "bad radius / max_neighbors");
+  if (static_cast<int64_t>(max_neighbors) * scan->n > pr->counts[0]) return Fail(ctx, NLO_EINVAL, "problem capacity too small");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = MatchInto(ctx, scan, map, pose, radius, max_neighbors, pr, scan->d_matched);
+  if (rc != NLO_OK) return rc;
+  unsigned long long m = 0;
+  NLO_CUDA(ctx, cudaMemcpyAsync(ctx->host_small, scan->d_matched, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(&m, ctx->host_small, sizeof(m));
+  if (matched) *matched = static_cast<int64_t>(m);
+  return NLO_OK;
+}
+
+int nlo_ndt_register(nlo_context* ctx, const nlo_scan* scan_in, const nlo_ndt_map* map, const nlo_solve_options* options,
+                     double radius, int32_t max_neighbors, int32_t max_outer, int32_t three_dof, double pose[16],
+                     nlo_register_result* result) {
+  if (ctx == nullptr || scan_in == nullptr || map == nullptr || options == nullptr || pose == nullptr || result == nullptr)
+    return Fail(ctx, NLO_EINVAL, "null argument");
+  if (max_neighbors < 1 || max_neighbors > 2 || !(radius > 0.0) || max_outer < 0) return Fail(ctx, NLO_EINVAL, "bad argument");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  nlo_scan* scan = const_cast<nlo_scan*>(scan_in);
+  const int64_t need = static_cast<int64_t>(max_neighbors) * scan->n;
+  if (scan->workspace == nullptr || scan->workspace_capacity < need) {
+    if (scan->workspace) nlo_problem_destroy(ctx, scan->workspace);
+    scan->workspace = nullptr;
+    int rc = nlo_ndt_create(ctx, std::max<int64_t>(need, 1), &scan->workspace);
+    if (rc != NLO_OK) return rc;
+    scan->workspace_capacity = std::max<int64_t>(need, 1);
+  }
+  nlo_problem* pr = scan->workspace;
+  memset(result, 0, sizeof(*result));
+  cudaEvent_t e0, e1;
+  NLO_CUDA(ctx, cudaEventCreate(&e0));
+  NLO_CUDA(ctx, cudaEventCreate(&e1));
+  NLO_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  int rc = NLO_OK;
+  for (int outer = 0; outer < max_outer; ++outer) {
+    double last[16];
+    memcpy(last, pose, sizeof(last));
+    rc = MatchInto(ctx, scan, map, pose, radius, max_neighbors, pr, scan->d_matched);
+    if (rc != NLO_OK) break;
+    nlo_solve_result sr;
+    rc = Solve(ctx, pr, three_dof ? kNdt3 : kNdt6, options, pose, &sr, nullptr, false);
+    if (rc != NLO_OK) break;
+    result->outer_iterations = outer + 1;
+    result->inner_iterations += sr.iterations;
+    if (sr.iterations > 0 || outer == 0) result->final_cost = sr.final_cost;
+    // :495-499  pose_diff = last^-1 * current; stop on |dt| < 1e-5 and |dq.vec| < 1e-5
+    double Rl[9], tl[3], Rc[9], tc[3], Rd[9], td[3], q[4];
+    PoseToRt(last, Rl, tl);
+    PoseToRt(pose, Rc, tc);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        Rd[3 * r + c] = Rl[r] * Rc[c] + Rl[3 + r] * Rc[3 + c] + Rl[6 + r] * Rc[6 + c];
+      td[r] = Rl[r] * (tc[0] - tl[0]) + Rl[3 + r] * (tc[1] - tl[1]) + Rl[6 + r] * (tc[2] - tl[2]);
+    }
+    HostRotToQuat(Rd, q);
+    const double dt = std::sqrt(td[0] * td[0] + td[1] * td[1] + td[2] * td[2]);
+    const double dq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (dt < 1e-5 && dq < 1e-5) break;
+  }
+  cudaEventRecord(e1, ctx->stream);
+  unsigned long long m = 0;
+  cudaMemcpyAsync(ctx->host_small, scan->d_matched, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  memcpy(&m, ctx->host_small, sizeof(m));
+  result->matched = static_cast<int64_t>(m);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  result->device_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  result->status = rc;
+  return rc;
 }
 
 // ---- communicators ----

@@ -120,6 +120,43 @@ struct GenerateParams {
 };
 cudaError_t LaunchGenerateNdt(const GenerateParams& p, cudaStream_t stream);
 
+// Device NDT matcher (MatchPointCloud of the reference's test mains): for every scan point warped
+// by the pose, the <= max_neighbors nearest valid cell means within `radius`.
+struct MatchParams {
+  const double* scan[3];        // x y z planes of the scan (sensor frame)
+  int64_t n;                    // scan points
+  double* planes[kNdtPlanes];   // output correspondences: neighbour slot j of point i at j * n + i
+  double R[9], t[3];            // pose (row-major R)
+  double origin[3];
+  int dims[3];
+  double inv_voxel;
+  int reach;
+  double radius2;
+  int max_neighbors;            // 1 or 2
+  const double* cell_mean;
+  const double* cell_sqrt_info;
+  const unsigned char* cell_valid;
+  unsigned long long* matched;  // device counter of real (non-empty) correspondences
+};
+cudaError_t LaunchMatchNdt(const MatchParams& p, cudaStream_t stream);
+cudaError_t LaunchPackScan(const double* xyz, int64_t n, double* const planes[3], cudaStream_t stream);
+
+// Device NDT map builder (UpdateNdtMap of the reference's test mains) on a dense voxel grid.
+struct MapAccumParams {
+  const double* xyz;  // interleaved points
+  int64_t n;
+  double inv_voxel;
+  int kmin[3];
+  int dims[3];
+  int* count;       // [cells]
+  double* sums;     // [cells][9]: sum xyz (3) | moment xx xy xz yy yz zz (6)
+};
+cudaError_t LaunchMapBounds(const double* xyz, int64_t n, double inv_voxel, int* bounds6, cudaStream_t stream);
+cudaError_t LaunchMapAccumulate(const MapAccumParams& p, cudaStream_t stream);
+cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,
+                              double* cell_mean, double* cell_sqrt_info, unsigned char* cell_valid,
+                              cudaStream_t stream);
+
 }  // namespace nlo
 
 #endif  // NLO_INTERNAL_H_

@@ -16,6 +16,7 @@
 //   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_analytic_3dof.cc:29-99
 //   reprojection_error_minimizer/reprojection_error_minimizer_analytic.cc:26-100
 // and their SIMD / thread-pool twins (..._analytic_simd.cc:55-76,114-177).
+#include <climits>
 #include <cstdio>
 
 #include "nlo_device.cuh"
@@ -759,6 +760,233 @@ __global__ void generate_ndt_kernel(const GenerateParams g) {
 cudaError_t LaunchGenerateNdt(const GenerateParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   generate_ndt_kernel<<<GridFor(p.n, 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ device NDT matcher
+// Restates MatchPointCloud (mahalanobis_distance_minimizer/tests/simple_optimization_test.cc:296-342):
+// warp the point by the pose, take the (at most) two nearest valid cell means within the search
+// radius (flann radiusSearch with L2_Simple: squared distance < radius), emit one correspondence
+// per hit carrying the cell's mean and sqrt_information.  Instead of a KD-tree the dense voxel grid
+// is scanned `reach` cells around the point (a mean lies inside its own voxel, so every mean within
+// the radius is visited).  A missing neighbour becomes a zero-information record (exact zero
+// contribution), which keeps the output a fixed 2 x n layout with no compaction pass.
+__global__ void match_ndt_kernel(const MatchParams m) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  unsigned long long local_matched = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += stride) {
+    const double lx = m.scan[0][i], ly = m.scan[1][i], lz = m.scan[2][i];
+    const double wx = m.R[0] * lx + m.R[1] * ly + m.R[2] * lz + m.t[0];
+    const double wy = m.R[3] * lx + m.R[4] * ly + m.R[5] * lz + m.t[1];
+    const double wz = m.R[6] * lx + m.R[7] * ly + m.R[8] * lz + m.t[2];
+    const int cx = static_cast<int>(floor((wx - m.origin[0]) * m.inv_voxel));
+    const int cy = static_cast<int>(floor((wy - m.origin[1]) * m.inv_voxel));
+    const int cz = static_cast<int>(floor((wz - m.origin[2]) * m.inv_voxel));
+    int best[2] = {-1, -1};
+    double best_d2[2] = {m.radius2, m.radius2};
+    for (int oz = -m.reach; oz <= m.reach; ++oz) {
+      const int z = cz + oz;
+      if (z < 0 || z >= m.dims[2]) continue;
+      for (int oy = -m.reach; oy <= m.reach; ++oy) {
+        const int y = cy + oy;
+        if (y < 0 || y >= m.dims[1]) continue;
+        for (int ox = -m.reach; ox <= m.reach; ++ox) {
+          const int x = cx + ox;
+          if (x < 0 || x >= m.dims[0]) continue;
+          const int c = (z * m.dims[1] + y) * m.dims[0] + x;
+          if (!m.cell_valid[c]) continue;
+          const double ex = wx - m.cell_mean[3 * c], ey = wy - m.cell_mean[3 * c + 1],
+                       ez = wz - m.cell_mean[3 * c + 2];
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+          if (d2 < best_d2[0]) {
+            best_d2[1] = best_d2[0]; best[1] = best[0];
+            best_d2[0] = d2; best[0] = c;
+          } else if (d2 < best_d2[1]) {
+            best_d2[1] = d2; best[1] = c;
+          }
+        }
+      }
+    }
+    for (int j = 0; j < m.max_neighbors; ++j) {
+      const int64_t o = static_cast<int64_t>(j) * m.n + i;
+      const int c = best[j];
+      m.planes[0][o] = lx; m.planes[1][o] = ly; m.planes[2][o] = lz;
+      if (c >= 0) {
+        for (int k = 0; k < 3; ++k) m.planes[3 + k][o] = m.cell_mean[3 * c + k];
+        for (int k = 0; k < 9; ++k) m.planes[6 + k][o] = m.cell_sqrt_info[9 * c + k];
+        ++local_matched;
+      } else {
+        for (int k = 3; k < kNdtPlanes; ++k) m.planes[k][o] = 0.0;
+      }
+    }
+  }
+  if (m.matched != nullptr) {
+    for (int off = 16; off > 0; off >>= 1) local_matched += __shfl_xor_sync(0xffffffffu, local_matched, off);
+    if ((threadIdx.x & 31) == 0 && local_matched) atomicAdd(m.matched, local_matched);
+  }
+}
+
+cudaError_t LaunchMatchNdt(const MatchParams& p, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  match_ndt_kernel<<<GridFor(p.n, 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+__global__ void pack_scan_kernel(const double* __restrict__ xyz, int64_t n, double* px, double* py, double* pz) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    px[i] = xyz[3 * i]; py[i] = xyz[3 * i + 1]; pz[i] = xyz[3 * i + 2];
+  }
+}
+cudaError_t LaunchPackScan(const double* xyz, int64_t n, double* const planes[3], cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pack_scan_kernel<<<GridFor(n, 256), 256, 0, stream>>>(xyz, n, planes[0], planes[1], planes[2]);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ device NDT map builder
+// UpdateNdtMap (tests/simple_optimization_test.cc:236-280) on a dense voxel grid.
+__global__ void map_bounds_kernel(const double* __restrict__ xyz, int64_t n, double inv_voxel, int* bounds6) {
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    for (int a = 0; a < 3; ++a) {
+      const int k = static_cast<int>(floor(xyz[3 * i + a] * inv_voxel));
+      lo[a] = min(lo[a], k);
+      hi[a] = max(hi[a], k);
+    }
+  for (int a = 0; a < 3; ++a) {
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bounds6 + a, lo[a]);
+      atomicMax(bounds6 + 3 + a, hi[a]);
+    }
+  }
+}
+
+__global__ void map_accumulate_kernel(const MapAccumParams m) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += stride) {
+    const double x = m.xyz[3 * i], y = m.xyz[3 * i + 1], z = m.xyz[3 * i + 2];
+    const int kx = static_cast<int>(floor(x * m.inv_voxel)) - m.kmin[0];
+    const int ky = static_cast<int>(floor(y * m.inv_voxel)) - m.kmin[1];
+    const int kz = static_cast<int>(floor(z * m.inv_voxel)) - m.kmin[2];
+    const int64_t c = (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
+    atomicAdd(m.count + c, 1);
+    double* s = m.sums + 9 * c;
+    atomicAdd(s + 0, x); atomicAdd(s + 1, y); atomicAdd(s + 2, z);
+    atomicAdd(s + 3, x * x); atomicAdd(s + 4, x * y); atomicAdd(s + 5, x * z);
+    atomicAdd(s + 6, y * y); atomicAdd(s + 7, y * z); atomicAdd(s + 8, z * z);
+  }
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (row-major a[9]); eigenvalues ascending in
+// w, eigenvectors in the COLUMNS of V.  Each eigenvector is sign-normalised so that its
+// largest-magnitude component is positive (the decomposition is otherwise unique only up to sign).
+__device__ inline void SymmetricEigen3(const double* a_in, double* w, double* V) {
+  double a[9];
+  for (int i = 0; i < 9; ++i) { a[i] = a_in[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    const double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[3 * p + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[3 * q + q] - a[3 * p + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[3 * k + p], akq = a[3 * k + q];
+          a[3 * k + p] = c * akp - s * akq;
+          a[3 * k + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[3 * p + k], aqk = a[3 * q + k];
+          a[3 * p + k] = c * apk - s * aqk;
+          a[3 * q + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+          V[3 * k + p] = c * vkp - s * vkq;
+          V[3 * k + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2 - i; ++j)
+      if (w[j] > w[j + 1]) {
+        const double tw = w[j]; w[j] = w[j + 1]; w[j + 1] = tw;
+        for (int k = 0; k < 3; ++k) { const double tv = V[3 * k + j]; V[3 * k + j] = V[3 * k + j + 1]; V[3 * k + j + 1] = tv; }
+      }
+  for (int j = 0; j < 3; ++j) {
+    int big = 0;
+    for (int k = 1; k < 3; ++k) if (fabs(V[3 * k + j]) > fabs(V[3 * big + j])) big = k;
+    if (V[3 * big + j] < 0.0) for (int k = 0; k < 3; ++k) V[3 * k + j] = -V[3 * k + j];
+  }
+}
+
+__global__ void map_finalize_kernel(const int* __restrict__ count, const double* __restrict__ sums, int64_t cells,
+                                    int v_not_transposed, double* cell_mean, double* cell_sqrt_info,
+                                    unsigned char* cell_valid) {
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= cells) return;
+  double mean[3] = {0, 0, 0}, S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned char valid = 0;
+  const int n = count[c];
+  if (n >= 5) {  // :250-253
+    const double inv_n = 1.0 / n;
+    const double* s = sums + 9 * c;
+    for (int a = 0; a < 3; ++a) mean[a] = s[a] * inv_n;
+    // moment starts at Identity (types.h:14): cov = (I + sum p p^T) / n - mean mean^T
+    double cov[9];
+    cov[0] = (s[3] + 1.0) * inv_n - mean[0] * mean[0];
+    cov[1] = cov[3] = s[4] * inv_n - mean[0] * mean[1];
+    cov[2] = cov[6] = s[5] * inv_n - mean[0] * mean[2];
+    cov[4] = (s[6] + 1.0) * inv_n - mean[1] * mean[1];
+    cov[5] = cov[7] = s[7] * inv_n - mean[1] * mean[2];
+    cov[8] = (s[8] + 1.0) * inv_n - mean[2] * mean[2];
+    double w[3], V[9];
+    SymmetricEigen3(cov, w, V);
+    if (w[2] >= 0.01) {  // :263
+      valid = 1;
+      w[0] = fmax(w[0], 0.01 * w[2]);  // :271-272
+      w[1] = fmax(w[1], 0.01 * w[2]);
+      for (int r = 0; r < 3; ++r) {
+        const double d = 1.0 / sqrt(w[r]);
+        for (int col = 0; col < 3; ++col)  // diag * V as the reference writes it (:275-276), or diag * V^T
+          S[3 * r + col] = d * (v_not_transposed ? V[3 * r + col] : V[3 * col + r]);
+      }
+    } else {
+      mean[0] = mean[1] = mean[2] = 0.0;
+    }
+  }
+  for (int a = 0; a < 3; ++a) cell_mean[3 * c + a] = valid ? mean[a] : 0.0;
+  for (int k = 0; k < 9; ++k) cell_sqrt_info[9 * c + k] = S[k];
+  cell_valid[c] = valid;
+}
+
+cudaError_t LaunchMapBounds(const double* xyz, int64_t n, double inv_voxel, int* bounds6, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  map_bounds_kernel<<<GridFor(n, 256), 256, 0, stream>>>(xyz, n, inv_voxel, bounds6);
+  return cudaGetLastError();
+}
+cudaError_t LaunchMapAccumulate(const MapAccumParams& p, cudaStream_t stream) {
+  if (p.n <= 0) return cudaSuccess;
+  map_accumulate_kernel<<<GridFor(p.n, 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,
+                              double* cell_mean, double* cell_sqrt_info, unsigned char* cell_valid,
+                              cudaStream_t stream) {
+  if (cells <= 0) return cudaSuccess;
+  map_finalize_kernel<<<static_cast<int>((cells + 127) / 128), 128, 0, stream>>>(
+      count, sums, cells, v_not_transposed, cell_mean, cell_sqrt_info, cell_valid);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,39 @@
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck): every launch shape once."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nonlinear_optimizer_for_slam_b200 as nlo
+from nonlinear_optimizer_for_slam_b200 import synthetic as syn
+
+ctx = nlo.Context(0)
+grid = syn.room_ndt_grid(0.5)
+pose0 = nlo.identity_pose()
+ctx.set_loss(nlo.LOSS_EXPONENTIAL, [1.0, 1.0])
+# persistent cooperative path (grid > 1), resident and streaming tiles
+for n in (5000, 400000):
+    pr = nlo.NdtProblem(ctx, capacity=n)
+    pr.generate(n, 7, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), pose0, grid)
+    print("ndt6", n, pr.solve6(pose0, nlo.Options(max_iterations=6))["iterations"])
+    ctx.set_loss(nlo.LOSS_HUBER, [1.0])
+    print("ndt3", n, pr.solve3(pose0, nlo.Options(max_iterations=6))["iterations"])
+    print("assemble", pr.assemble6(pose0, 3, n - 5)[2])
+    ctx.set_loss(nlo.LOSS_EXPONENTIAL, [1.0, 1.0])
+    pr.close()
+# in-CTA loop (<= 3 tiles) and batched
+pr = nlo.NdtProblem(ctx, capacity=600)
+pr.generate(600, 8, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), pose0, grid)
+print("tiny", pr.solve6(pose0, nlo.Options(max_iterations=6))["iterations"])
+pr.close()
+pr = nlo.NdtProblem(ctx, counts=[3000, 100, 2049])
+pr.generate_batched(9, 0.01, np.tile(syn.to_pose16(syn.CFG1_TRUE), (3, 1)), pose0, grid)
+print("batched", pr.solve6_batched(np.tile(pose0, (3, 1)), nlo.Options(max_iterations=6))["iterations"])
+pr.close()
+X, px, K = syn.pnp_fixture()
+pr = nlo.ReprojProblem(ctx, capacity=len(X)); pr.upload(X, px, K)
+print("pnp", pr.solve(pose0)["iterations"])
+pr.close()
+ctx.close()
+print("SANITIZE_CASE_DONE")
