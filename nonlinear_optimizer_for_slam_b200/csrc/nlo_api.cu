@@ -106,6 +106,7 @@ struct nlo_context {
   PeerComm peer{};
   unsigned long long* d_peer_seq = nullptr;
   int* d_peer_error = nullptr;
+  unsigned long long* d_debug_times = nullptr;  // NLO_DEBUG_TIMES=1: [64][8] stamps of the last loop
   int generation = 0;  // bumped whenever cached graphs become stale (loss / comm change)
 };
 
@@ -268,6 +269,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   p.gradient_tolerance = 1e-6;
   p.max_iterations = 1;
   p.iterations_in_kernel = 1;
+  p.debug_times = ctx->d_debug_times;
   p.use_peer = (ctx->comm_kind == kCommPeer) ? 1 : 0;
   p.peer = ctx->peer;
   return p;
@@ -484,6 +486,19 @@ int Solve(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* 
   NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   NLO_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (ctx->d_debug_times != nullptr && options->max_iterations >= 8 && options->max_iterations <= 64) {
+    std::vector<unsigned long long> ts(64 * 8);
+    cudaMemcpy(ts.data(), ctx->d_debug_times, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    // average phase durations over iterations 2..7 (ns): tiles | cta-sync | barrier | x-cta sum | step | sync
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double period = 0;
+    for (int it = 2; it < 8; ++it) {
+      for (int k = 0; k < 6; ++k) acc[k] += static_cast<double>(ts[it * 8 + k + 1]) - static_cast<double>(ts[it * 8 + k]);
+      period += static_cast<double>(ts[(it + 1) * 8]) - static_cast<double>(ts[it * 8]);
+    }
+    fprintf(stderr, "[nlo debug] ns/iter: tiles %.0f | cta-sync %.0f | barrier %.0f | x-cta-sum %.0f | canon+step %.0f | sync %.0f | period %.0f\n",
+            acc[0] / 6, acc[1] / 6, acc[2] / 6, acc[3] / 6, acc[4] / 6, acc[5] / 6, period / 6);
+  }
   int rc_all = NLO_OK;
   for (int k = 0; k < B; ++k) {
     results[k].iterations = static_cast<int32_t>(res[4 * k]);
@@ -525,6 +540,11 @@ int nlo_context_create(int device, nlo_context** out) {
   ctx->grid_small = prop.multiProcessorCount;
   const char* sgenv = getenv("NLO_GRID_SMALL");
   if (sgenv != nullptr && atoi(sgenv) > 0) ctx->grid_small = atoi(sgenv);
+  const char* denv = getenv("NLO_DEBUG_TIMES");
+  if (denv != nullptr && denv[0] == '1') {
+    cudaMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), 64 * 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_debug_times, 0, 64 * 8 * sizeof(unsigned long long));
+  }
   const char* genv = getenv("NLO_GRID");
   if (genv != nullptr && atoi(genv) > 0) ctx->grid_single = atoi(genv);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -545,6 +565,7 @@ int nlo_context_destroy(nlo_context* ctx) {
   nlo_comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->d_debug_times) cudaFree(ctx->d_debug_times);
   if (ctx->host_small) cudaFreeHost(ctx->host_small);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -72,6 +72,7 @@ struct IterParams {
   int iterations_in_kernel;  // > 1 only when grid.x == 1 (whole loop inside one CTA)
   int mode;
   int use_peer;
+  unsigned long long* debug_times;  // nullable: [iterations][8] globaltimer stamps of CTA 0 (profiling aid)
   int persistent;  // cooperative launch: the whole loop in one grid, grid barrier per iteration
   PeerComm peer;
 };

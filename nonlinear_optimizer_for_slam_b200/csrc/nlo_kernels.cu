@@ -214,6 +214,13 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
   const bool writer = (blockIdx.x == 0) || !p.persistent;  // who publishes state / trace / sums
 
+  // profiling aid (NLO_DEBUG_TIMES=1): CTA 0 / thread 0 stamps the phases of each iteration
+#define NLO_STAMP(slot)                                                                  \
+  do {                                                                                   \
+    if (p.debug_times != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)      \
+      p.debug_times[static_cast<size_t>(it) * 8 + (slot)] = GlobalTimerNs();             \
+  } while (0)
+
   uint32_t ring = 0;  // tiles consumed so far by this CTA (keeps mbarrier phases across iterations)
   // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
   // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
@@ -221,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
 
   for (int it = 0; it < p.iterations_in_kernel; ++it) {
     if (st.done) break;  // uniform: the state only changes behind a __syncthreads
+    NLO_STAMP(0);
 
     if (p.mode != kModeStepOnly) {
       double acc[NACC];
@@ -298,7 +306,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
         }
       }
       if (!resident) ring += my_tiles;
+      NLO_STAMP(1);
       __syncthreads();
+      NLO_STAMP(2);
 
       // CTA sum over the 8 consumer warps, fixed order
       if (tid < NACC) {
@@ -313,7 +323,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
             p.partials + static_cast<size_t>((it & 1) * gridDim.y + problem) * grid_x * NACC;
         if (tid < NACC) {
           __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, sm.total[tid]);
-          __threadfence();
+          // persistent path: the releasing fence of thread 0 inside GridBarrier (after its
+          // bar.sync) covers these stores by cumulativity; the ticket path fences per writer
+          if (!p.persistent) __threadfence();
         }
         if (p.persistent) {
           // every CTA waits for all partials, then reduces and steps redundantly (no broadcast)
@@ -333,12 +345,22 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           if (sm.flag == 0) return;  // only the last CTA to arrive carries on
           __threadfence();
         }
+        NLO_STAMP(3);
         // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
         const int j = tid >> 3, l8 = tid & 7;
         if (j < NACC) {
           const double* base = partial_base + j;
           double s = 0.0;
-          for (int g = l8; g < grid_x; g += 8) s += __ldcg(base + static_cast<size_t>(g) * NACC);
+          int g = l8;
+          // loads are issued 8 at a time (independent addresses), the adds keep the fixed order
+          for (; g + 56 < grid_x; g += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + static_cast<size_t>(g + 8 * u) * NACC);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+          }
+          for (; g < grid_x; g += 8) s += __ldcg(base + static_cast<size_t>(g) * NACC);
           sm.warp_sums[l8][j] = s;
         }
         __syncthreads();
@@ -351,11 +373,13 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       }
       __syncthreads();
 
+      NLO_STAMP(4);
       // raw -> canonical (needs the R the sums were taken at)
-      if (tid == 0 && KIND != kNdt3) {
-        double canon[kAcc6];
-        Canonical6(sm.total, st.R, canon);
-        for (int k = 0; k < kAcc6; ++k) sm.total[k] = canon[k];
+      if (KIND != kNdt3) {
+        double canon = 0.0;
+        if (tid < kAcc6) canon = Canonical6Entry(tid, sm.total, st.R);
+        __syncthreads();
+        if (tid < kAcc6) sm.total[tid] = canon;
       }
       __syncthreads();
       if (p.use_peer) PeerAllReduce(p.peer, sm.total, NACC);
@@ -382,8 +406,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
               trace_row);
       if (writer) *st_global = st;
     }
+    NLO_STAMP(5);
     __syncthreads();
+    NLO_STAMP(6);
   }
+#undef NLO_STAMP
 }
 
 // ------------------------------------------------------------------ dispatch

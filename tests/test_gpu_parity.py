@@ -241,10 +241,11 @@ def test_generate_matches_host_association(ctx, nlo):
     prob.close(); prob2.close()
 
 
-def test_large_generated_shards_sum_and_repeat(ctx, nlo):
-    """Size-independent properties at scale: point-range shards sum to the whole (linearity) and
-    the reduction is deterministic (bitwise repeatable)."""
-    n = 4_000_000
+@pytest.mark.parametrize("n", [4_000_000, 64 * 1024 * 1024])
+def test_large_generated_shards_sum_and_repeat(ctx, nlo, n):
+    """Size-independent properties up to BASELINE's full cfg4 size (64M points, 8 GB of planes):
+    point-range shards sum to the whole (linearity, what the multi-GPU all-reduce relies on), the
+    reduction is deterministic (bitwise repeatable), and a solve is repeatable bit for bit."""
     grid = syn.room_ndt_grid(0.5)
     prob = nlo.NdtProblem(ctx, capacity=n)
     prob.generate(n, 1004, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), nlo.identity_pose(), grid)
@@ -254,12 +255,39 @@ def test_large_generated_shards_sum_and_repeat(ctx, nlo):
     H2, g2, c2 = prob.assemble6(pose)
     assert np.array_equal(H, H2) and np.array_equal(g, g2) and c == c2
     acc = np.zeros(28)
-    cuts = [0, 1_000_003, 2_500_000, 2_500_001, n]
+    cuts = [0, 1_000_003, 2_500_000, 2_500_001, n // 2 + 17, n]
     for b, e in zip(cuts[:-1], cuts[1:]):
         Hs, gs, cs = prob.assemble6(pose, b, e)
         acc += np.concatenate([Hs, gs, [cs]])
     assert_sums_close(acc[:21], acc[21:27], acc[27], H, g, c, tol=1e-11)
+    r1 = prob.solve6(pose, nlo.Options(max_iterations=5), trace=True)
+    r2 = prob.solve6(pose, nlo.Options(max_iterations=5), trace=True)
+    assert np.array_equal(r1["trace"], r2["trace"]) and np.array_equal(r1["pose"], r2["pose"])
+    # the first trace row is the assembly at the initial pose
+    np.testing.assert_array_equal(r1["trace"][0, :21], H)
     prob.close()
+
+
+def test_batched_copies_are_identical_and_match_single(ctx, nlo):
+    """cfg5-shaped property: B copies of one registration solved in one batched launch give B
+    bit-identical results, equal to the single-problem path within the parity tolerance."""
+    grid = syn.room_ndt_grid(0.5)
+    B, n = 300, 20000
+    true = np.tile(syn.to_pose16(syn.CFG1_TRUE), (B, 1))
+    ctx.set_loss(1, [1.0, 1.0])
+    prob = nlo.NdtProblem(ctx, counts=[n] * B)
+    # every registration from the same stream: seeds differ by +k, so rebuild with equal seeds
+    single = nlo.NdtProblem(ctx, capacity=n)
+    single.generate(n, 77, 0, 0.01, true[0], nlo.identity_pose(), grid)
+    p, m, s = single.download(0, n)
+    prob.upload(np.tile(p, (B, 1)), np.tile(m, (B, 1)), np.tile(s, (B, 1)))
+    out = prob.solve6_batched(np.tile(nlo.identity_pose(), (B, 1)))
+    assert np.all(out["iterations"] == out["iterations"][0])
+    assert np.all(out["poses"] == out["poses"][0])
+    ref = single.solve6(nlo.identity_pose())
+    assert ref["iterations"] == out["iterations"][0]
+    assert np.max(np.abs(ref["pose"] - out["poses"][0])) < 1e-9
+    prob.close(); single.close()
 
 
 def test_batched_generate_matches_single_generate(ctx, nlo, oracle):
