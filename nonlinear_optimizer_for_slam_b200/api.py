@@ -171,6 +171,7 @@ class NdtProblem(_Problem):
     def __init__(self, ctx, capacity=None, counts=None):
         super().__init__(ctx)
         self.batched = counts is not None
+        self.counts = None
         if self.batched:
             self.counts = np.ascontiguousarray(counts, dtype=np.int64)
             ctx._check(self._lib.nlo_ndt_create_batched(
@@ -248,6 +249,8 @@ class NdtProblem(_Problem):
 
     def solve6_batched(self, poses, options=None):
         options = options or Options()
+        if not self.batched:
+            raise NloError(-1, "solve6_batched needs a problem created with counts=[...]")
         B = len(self.counts)
         poses = _f64(poses).reshape(B, 16).copy()
         opt = options._c()

@@ -232,8 +232,8 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
   NLO_CUDA_P(cudaMalloc(&pr->d_partials,
                         2 * static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double)));
-  NLO_CUDA_P(cudaMalloc(&pr->d_barrier, slots * sizeof(unsigned int)));
-  NLO_CUDA_P(cudaMemsetAsync(pr->d_barrier, 0, slots * sizeof(unsigned int), ctx->stream));
+  NLO_CUDA_P(cudaMalloc(&pr->d_barrier, 2 * slots * sizeof(unsigned int)));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_barrier, 0, 2 * slots * sizeof(unsigned int), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_tickets, 0, slots * sizeof(unsigned int), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
@@ -276,7 +276,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
 }
 
 bool UsePersistent(const nlo_context* ctx, const nlo_problem* pr) {
-  return ctx->use_persistent && ctx->comm_kind == kCommNone && !pr->batched;
+  return ctx->use_persistent && ctx->comm_kind != kCommNccl && !pr->batched;
 }
 
 int GridFor(nlo_context* ctx, int64_t begin, int64_t end) {
@@ -370,7 +370,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     p.mode = kModeSolve;
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
-    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, sizeof(unsigned int), ctx->stream));
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, 2 * sizeof(unsigned int), ctx->stream));
     NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream));
     return NLO_OK;
   }
@@ -395,7 +395,8 @@ int RunLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options
   // NCCL calls are left out of graph capture (their capture support depends on the library
   // build); the other paths run as one CUDA graph so the loop needs a single host call.
   const int64_t tiles_all = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
-  const bool single_launch = (ctx->comm_kind == kCommNone) && (pr->batched || tiles_all <= kInCtaTiles || UsePersistent(ctx, pr));
+  const bool single_launch = UsePersistent(ctx, pr) ||
+                             ((ctx->comm_kind == kCommNone) && (pr->batched || tiles_all <= kInCtaTiles));
   const bool graph = ctx->use_graph && ctx->comm_kind != kCommNccl && !single_launch;
   if (!graph) return EnqueueLoop(ctx, pr, kind, opt, with_trace, num_problems, begin_abs, end_abs);
   int64_t ptol_bits, gtol_bits;

@@ -62,7 +62,7 @@ struct IterParams {
   State* states;        // [num_problems]
   double* partials;     // [2 parities][num_problems][grid.x][nacc]
   unsigned int* tickets;  // [num_problems] last-CTA election of the one-iteration-per-launch path
-  unsigned int* barrier;  // [num_problems] grid barrier of the persistent path (0 at launch)
+  unsigned int* barrier;  // [num_problems][2] persistent path: arrival counter | published state sequence (0 at launch)
   double* sums;           // [num_problems][32] canonical H|g|cost (out for assemble, in for step-only)
   double* trace;          // nullable: [num_problems][max_iterations][trace_width]
   double loss_p0, loss_p1;

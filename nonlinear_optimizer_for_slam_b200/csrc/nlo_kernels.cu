@@ -150,30 +150,6 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
   __syncthreads();
 }
 
-// Grid-wide barrier for the persistent (cooperative-launch) path: `counter` starts at 0 for the
-// launch and only grows; barrier k completes when it reaches k * gridDim.x.  All CTAs are
-// co-resident (cudaLaunchCooperativeKernel), so spinning is safe; a 2 s timeout turns a lost CTA
-// into an error flag instead of a hang.
-__device__ __forceinline__ bool GridBarrier(unsigned int* counter, unsigned int target) {
-  __shared__ int ok;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ok = 1;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned long long start = GlobalTimerNs();
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
-      if (GlobalTimerNs() - start > 2000000000ULL) {
-        ok = 0;
-        break;
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  return ok != 0;
-}
-
 template <int KIND, int LOSS>
 __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
@@ -225,6 +201,10 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
   // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
   const bool resident = (p.iterations_in_kernel > 1) && (my_tiles <= STAGES);
+  // Streaming case: the first tiles of the NEXT iteration (the same tiles, they do not depend on
+  // the pose) are requested before this iteration's reduction / step, which hides the pipeline
+  // ramp behind the grid-wide exchange.  `prefetched` tiles of the coming iteration are in flight.
+  int prefetched = 0;
 
   for (int it = 0; it < p.iterations_in_kernel; ++it) {
     if (st.done) break;  // uniform: the state only changes behind a __syncthreads
@@ -251,8 +231,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
         };
         const bool need_load = !resident || it == 0;
         if (tid == 0 && need_load) {
-          for (int m = 0; m < STAGES - 1 && m < my_tiles; ++m) issue_tile(m);
+          for (int m = prefetched; m < STAGES - 1 && m < my_tiles; ++m) issue_tile(m);
         }
+        prefetched = 0;
         __syncwarp();
         double R[9], t[3];
         if (KIND == kNdt3) {
@@ -304,8 +285,16 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
 #pragma unroll
           for (int k = 0; k < NACC; ++k) sm.warp_sums[warp][k] = acc[k];
         }
+        if (!resident) {
+          ring += my_tiles;
+          if (it + 1 < p.iterations_in_kernel && p.mode == kModeSolve) {
+            const int ahead = (my_tiles < STAGES - 1) ? my_tiles : STAGES - 1;
+            if (tid == 0)
+              for (int m = 0; m < ahead; ++m) issue_tile(m);
+            prefetched = ahead;
+          }
+        }
       }
-      if (!resident) ring += my_tiles;
       NLO_STAMP(1);
       __syncthreads();
       NLO_STAMP(2);
@@ -323,16 +312,52 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
             p.partials + static_cast<size_t>((it & 1) * gridDim.y + problem) * grid_x * NACC;
         if (tid < NACC) {
           __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, sm.total[tid]);
-          // persistent path: the releasing fence of thread 0 inside GridBarrier (after its
-          // bar.sync) covers these stores by cumulativity; the ticket path fences per writer
+          // persistent path: thread 0's releasing fence after the bar.sync below covers these
+          // stores by cumulativity; the ticket path fences per writer
           if (!p.persistent) __threadfence();
         }
         if (p.persistent) {
-          // every CTA waits for all partials, then reduces and steps redundantly (no broadcast)
-          if (!GridBarrier(p.barrier + problem, static_cast<unsigned int>(it + 1) * grid_x)) {
-            if (tid == 0) { st.status = 2; st.done = 1; if (writer) *st_global = st; }
+          // Persistent grid: every CTA arrives on a counter; CTA 0 (the leader) waits for all
+          // partials, reduces them, [all-reduces over NVLink], steps and PUBLISHES the new state
+          // with a sequence word; the other CTAs wait for that word and reload the 160-byte state.
+          unsigned int* counter = p.barrier + 2 * problem;
+          unsigned int* state_seq = counter + 1;
+          const unsigned int want = static_cast<unsigned int>(it) + 1u;
+          __syncthreads();
+          if (tid == 0) {
+            __threadfence();  // releases this CTA's partial (cumulative over the bar.sync above)
+            atomicAdd(counter, 1u);
+            sm.flag = 1;
+            const unsigned long long start = GlobalTimerNs();
+            if (blockIdx.x == 0) {
+              while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
+                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
+            } else {
+              while (*reinterpret_cast<volatile unsigned int*>(state_seq) < want)
+                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
+            }
+            __threadfence();
+          }
+          __syncthreads();
+          if (sm.flag == 0) {  // a CTA went missing (cannot happen under a cooperative launch)
+            if (tid == 0) {
+              st.status = 2;
+              st.done = 1;
+              if (blockIdx.x == 0) {
+                *st_global = st;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned int*>(state_seq) = want;
+              }
+            }
             __syncthreads();
             break;
+          }
+          if (blockIdx.x != 0) {
+            if (tid < static_cast<int>(sizeof(State) / sizeof(double)))
+              reinterpret_cast<double*>(&st)[tid] =
+                  __ldcg(reinterpret_cast<const double*>(st_global) + tid);
+            __syncthreads();
+            continue;
           }
         } else {
           __syncthreads();
@@ -392,25 +417,41 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       __syncthreads();
     }
 
-    // ---------------- damped step, one thread (redundantly per CTA in the persistent path)
-    if (tid == 0) {
+    // ---------------- damped step by warp 0 (redundantly per CTA in the persistent path)
+    if (warp == 0) {
       double* trace_row = nullptr;
       if (p.trace != nullptr && writer)
         trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st.iteration) *
                                   T::kTrace;
-      if (KIND == kNdt3)
-        Step3(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
-              trace_row);
-      else
-        Step6(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
-              trace_row);
-      if (writer) *st_global = st;
+      if (lane == 0) {
+        if (KIND == kNdt3)
+          Step3(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+                trace_row);
+        else
+          Step6(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+                trace_row);
+      }
+      if (lane == 0 && writer) {
+        *st_global = st;
+        if (p.persistent && grid_x > 1) {  // publish to the follower CTAs
+          __threadfence();
+          *reinterpret_cast<volatile unsigned int*>(p.barrier + 2 * problem + 1) =
+              static_cast<unsigned int>(it) + 1u;
+        }
+      }
     }
     NLO_STAMP(5);
     __syncthreads();
     NLO_STAMP(6);
   }
 #undef NLO_STAMP
+  // a prefetch may still be in flight when the loop ends early: let it land before the CTA exits
+  if (prefetched > 0) {
+    for (int m = 0; m < prefetched; ++m) {
+      const uint32_t k = ring + m;
+      MbarWait(&sm.full[k % STAGES], (k / STAGES) & 1u);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ dispatch
