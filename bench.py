@@ -267,11 +267,14 @@ def run_cuda(args):
     assert res["iterations"] == args.steps, res
     ms_local = res["device_ms"]  # CUDA events on the context stream around the K-iteration loop
     ms = ms_local
+    per_rank_ms = [ms_local]
     if dist is not None:
         import torch
         tms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
+        per_rank_ms = [None] * world
+        dist.all_gather_object(per_rank_ms, ms_local)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
     value = total * args.steps / (ms * 1e-3) / 1e9
@@ -300,16 +303,17 @@ def run_cuda(args):
                "scalar_f64_gpoints_s": rates["scalar_f64"]["gpoints_s"]}
 
     if rank == 0:
-        # N = 1: the whole K-iteration loop is ONE persistent cooperative launch of
-        # gn_iteration_kernel (grid barrier per iteration); peer: one launch per iteration;
+        # the whole K-iteration loop is ONE persistent cooperative launch of gn_iteration_kernel per
+        # GPU (leader CTA reduces, [peer all-reduce over NVLink], steps, publishes the state);
         # nccl: assemble + step kernels per iteration (plus NCCL's own kernel, not counted)
-        launches = 1 if world == 1 else (args.steps if comm == "peer" else 2 * args.steps)
+        launches = 1 if comm != "nccl" else 2 * args.steps
         line = {
             "metric": "NDT 6-DoF assembly Gpoints/s", "value": value, "unit": "Gpoints/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gn_iterations_per_s": iters_per_s,
+            "per_rank_ms_per_step": [round(v / args.steps, 6) for v in per_rank_ms],
             "config": {"workload": "cfg4: NDT 6-DoF, %d-point scan vs 0.5 m-voxel NDT map, "
                                    "Exponential(1,1), sharded by point range" % total,
                        "points_total": total, "points_per_gpu": n_local, "comm": comm,
@@ -317,10 +321,10 @@ def run_cuda(args):
                              % (n_local * BYTES_PER_CORR / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(n_local, args.steps if world == 1 else 1),
+                         "traffic": ncu_traffic_per_launch(n_local, args.steps if comm != "nccl" else 1),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_iteration": n_local * BYTES_PER_CORR,
-                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR * (args.steps if world == 1 else 1),
+                         "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR * (args.steps if comm != "nccl" else 1),
                          "kernel": "gn_iteration_kernel<ndt6, exponential>"},
             "cpu_baseline": cpu,
             "e2e": e2e,

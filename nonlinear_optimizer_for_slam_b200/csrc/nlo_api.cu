@@ -72,9 +72,7 @@ bool LoadNccl(NcclApi* api, std::string* err) {
 
 enum CommKind { kCommNone = 0, kCommNccl = 1, kCommPeer = 2 };
 
-constexpr size_t kPeerSlotBytes = 2 * kMaxRanks * 32 * sizeof(double);
-constexpr size_t kPeerFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
-constexpr size_t kPeerBufBytes = kPeerSlotBytes + kPeerFlagBytes;
+constexpr size_t kPeerBufBytes = 2 * kMaxRanks * kPeerWords * sizeof(unsigned long long);
 
 constexpr int kInCtaTiles = 3;  // a registration this small runs its whole loop inside one CTA
 constexpr int kSmallDoubles = 8192;  // pinned + device scratch for poses / sums / results
@@ -1246,8 +1244,7 @@ int nlo_comm_peer_init(nlo_context* ctx, const uint8_t* handles, int32_t rank, i
       ctx->peer_opened[r] = ptr;
       base = static_cast<unsigned char*>(ptr);
     }
-    pc.slots[r] = reinterpret_cast<double*>(base);
-    pc.flags[r] = reinterpret_cast<unsigned long long*>(base + kPeerSlotBytes);
+    pc.slots[r] = reinterpret_cast<unsigned long long*>(base);
   }
   pc.seq = ctx->d_peer_seq;
   pc.error = ctx->d_peer_error;

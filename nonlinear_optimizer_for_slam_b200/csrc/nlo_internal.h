@@ -17,6 +17,7 @@ constexpr int kReprojPlanes = 5;      // X Y Z | u v
 constexpr int kAcc6 = 28;             // 21 H + 6 g + cost
 constexpr int kAcc3 = 10;             // 6 H + 3 g + cost
 constexpr int kMaxRanks = 8;
+constexpr int kPeerWords = 64;        // 8-byte words per (parity, source rank) slot of the peer exchange
 
 // Per-registration optimisation state, resident in HBM for the whole solve.
 //   6-DoF / reprojection: t[3], q[4] (x,y,z,w), R = row-major rotation of q.
@@ -39,13 +40,12 @@ struct Range {
 };
 
 // One-shot all-reduce over peer-mapped buffers (NVLink / NVSwitch).
-//   slots[r] points into rank r's exchange buffer: [2 parities][kMaxRanks sources][32 doubles]
-//   flags[r] points into rank r's flag array:       [2 parities][kMaxRanks sources] (uint64 seq)
+//   slots[r] points into rank r's exchange buffer: [2 parities][kMaxRanks sources][kPeerWords] of
+//   8-byte words, each = (sequence number << 32) | 32 payload bits
 struct PeerComm {
   int rank;
   int nranks;
-  double* slots[kMaxRanks];
-  unsigned long long* flags[kMaxRanks];
+  unsigned long long* slots[kMaxRanks];
   unsigned long long* seq;  // local, device: exchange sequence number (monotonic)
   int* error;               // local, device: set to 1 if a wait timed out
 };

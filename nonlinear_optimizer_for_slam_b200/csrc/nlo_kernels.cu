@@ -107,42 +107,48 @@ constexpr size_t SmemBytes() {
 }
 
 // One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
-// finalising CTA.  Sum order is rank 0..n-1 on every rank => bit-identical results everywhere.
+// finalising CTA.  "LL" wire format: every 8-byte word carries 4 bytes of payload and the 4-byte
+// sequence number of the exchange, so a word is valid the moment its sequence matches -- one
+// NVLink one-way latency, no fences, no separate flag.  A double travels as two words.  Slots are
+// double-buffered by sequence parity (a rank can only be one exchange ahead of a peer).  The sum
+// runs in rank order 0..n-1 on every rank => bit-identical results everywhere.
 __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc) {
+  __shared__ unsigned int halves[kMaxRanks][kPeerWords];
   const int tid = threadIdx.x;
   const unsigned long long seq = *pc.seq + 1;
+  const unsigned int seq32 = static_cast<unsigned int>(seq);
   const int parity = static_cast<int>(seq & 1ULL);
-  const int slot = (parity * kMaxRanks + pc.rank) * 32;
-  if (tid < nacc) {
-    const double v = total[tid];
-    for (int r = 0; r < pc.nranks; ++r) {
-      volatile double* dst = pc.slots[r] + slot;
-      dst[tid] = v;
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (tid < pc.nranks) {
-    volatile unsigned long long* f = pc.flags[tid] + parity * kMaxRanks + pc.rank;
-    *f = seq;
-  }
-  if (tid < pc.nranks) {
-    volatile unsigned long long* f = pc.flags[pc.rank] + parity * kMaxRanks + tid;
+  const int words = 2 * nacc;
+  if (tid < words) {
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(total[tid >> 1]));
+    const unsigned long long half = (tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
+    const unsigned long long word = (static_cast<unsigned long long>(seq32) << 32) | half;
+    const int slot = (parity * kMaxRanks + pc.rank) * kPeerWords + tid;
+    for (int r = 0; r < pc.nranks; ++r)
+      *reinterpret_cast<volatile unsigned long long*>(pc.slots[r] + slot) = word;
     const unsigned long long start = GlobalTimerNs();
-    while (*f < seq) {
-      if (GlobalTimerNs() - start > 5000000000ULL) {  // 5 s: a peer died; fail instead of hanging
-        *pc.error = 1;
-        break;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const volatile unsigned long long* src =
+          reinterpret_cast<const volatile unsigned long long*>(pc.slots[pc.rank]) +
+          (parity * kMaxRanks + r) * kPeerWords + tid;
+      unsigned long long w = *src;
+      while (static_cast<unsigned int>(w >> 32) != seq32) {
+        if (GlobalTimerNs() - start > 5000000000ULL) {  // 5 s: a peer died; fail instead of hanging
+          *pc.error = 1;
+          break;
+        }
+        w = *src;
       }
+      halves[r][tid] = static_cast<unsigned int>(w);
     }
-    __threadfence_system();
   }
   __syncthreads();
   if (tid < nacc) {
     double s = 0.0;
     for (int r = 0; r < pc.nranks; ++r) {
-      const volatile double* src = pc.slots[pc.rank] + (parity * kMaxRanks + r) * 32;
-      s += src[tid];
+      const unsigned long long bits = (static_cast<unsigned long long>(halves[r][2 * tid + 1]) << 32) |
+                                      static_cast<unsigned long long>(halves[r][2 * tid]);
+      s += __longlong_as_double(static_cast<long long>(bits));
     }
     total[tid] = s;
   }
