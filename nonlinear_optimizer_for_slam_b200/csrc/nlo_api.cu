@@ -223,7 +223,8 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   } while (0)
   NLO_CUDA_P(cudaMalloc(&pr->plane_block, plane_bytes * pr->num_planes));
   NLO_CUDA_P(cudaMemsetAsync(pr->plane_block, 0, plane_bytes * pr->num_planes, ctx->stream));
-  for (int k = 0; k < pr->num_planes; ++k) pr->planes[k] = pr->plane_block + static_cast<size_t>(k) * pr->capacity;
+  // tile-interleaved layout: plane k of tile 0 starts at k * 256 (nlo_internal.h TiledOffset)
+  for (int k = 0; k < pr->num_planes; ++k) pr->planes[k] = pr->plane_block + static_cast<size_t>(k) * kTile;
   const int slots = num_problems + 1;
   pr->grid_x = batched ? 1 : ctx->grid_single;
   NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
@@ -757,7 +758,8 @@ int GenerateCommon(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t glo
   for (int b = 0; b < B; ++b) {
     const int64_t begin = pr->batched ? pr->h_ranges[b].begin : 0;
     const int64_t n = pr->batched ? pr->counts[b] : n_single;
-    for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k] + begin;
+    for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k];
+    g.dst_offset = begin;
     g.n = n;
     g.seed = seed + static_cast<uint64_t>(b);
     g.index_offset = pr->batched ? 0 : global_index_offset;

@@ -34,6 +34,15 @@ struct State {
   int pad;
 };
 
+// HBM layout of the correspondences: tile-interleaved SoA ("AoSoA").  Tile T (256 consecutive
+// correspondences) stores its NP planes back to back, [plane][256] doubles, so a whole tile is ONE
+// contiguous run of NP * 2 KB that a single TMA bulk copy moves into a shared-memory stage
+// unchanged.  planes[k] points at plane k of tile 0; element i of plane k lives at
+// planes[k][TiledOffset(NP, i)].
+__host__ __device__ inline int64_t TiledOffset(int nplanes, int64_t i) {
+  return (i >> 8) * (static_cast<int64_t>(nplanes) << 8) + (i & 255);
+}
+
 struct Range {
   int64_t begin;  // absolute index into the planes
   int64_t end;
@@ -105,6 +114,7 @@ cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int
 
 struct GenerateParams {
   double* planes[kNdtPlanes];
+  int64_t dst_offset;  // first correspondence index written (tile-aligned for batched problems)
   int64_t n;
   uint64_t seed;
   int64_t index_offset;

@@ -229,11 +229,10 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           const uint32_t phase = (k / STAGES) & 1u;
           MbarWait(&sm.empty[s], phase ^ 1u);
           MbarExpectTx(&sm.full[s], kStageBytes);
-          const int64_t first = (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile;
-#pragma unroll
-          for (int pl = 0; pl < NPLANES; ++pl)
-            BulkLoad(&sm.stages[s][pl][0], p.planes[pl] + first, kTile * sizeof(double),
-                     &sm.full[s]);
+          const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
+          // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy
+          BulkLoad(&sm.stages[s][0][0], p.planes[0] + tile * (NPLANES * kTile), kStageBytes,
+                   &sm.full[s]);
         };
         const bool need_load = !resident || it == 0;
         if (tid == 0 && need_load) {
@@ -604,7 +603,7 @@ __global__ void pack_ndt_kernel(const double* __restrict__ point, const double* 
                                 int64_t dst_offset) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t d = dst_offset + i;
+    const int64_t d = TiledOffset(kNdtPlanes, dst_offset + i);
 #pragma unroll
     for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * i + k];
 #pragma unroll
@@ -626,7 +625,7 @@ __global__ void pack_ndt_batched_kernel(const double* __restrict__ point,
   const int64_t dst0 = ranges[b].begin;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t s = src0 + i, d = dst0 + i;
+    const int64_t s = src0 + i, d = TiledOffset(kNdtPlanes, dst0 + i);
 #pragma unroll
     for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * s + k];
 #pragma unroll
@@ -642,17 +641,18 @@ __global__ void pack_ndt_aos_kernel(const unsigned char* __restrict__ records, i
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const unsigned char* rec = records + static_cast<size_t>(i) * stride_bytes;
+    const int64_t d = TiledOffset(kNdtPlanes, i);
     const double* pt = reinterpret_cast<const double*>(rec + off_point);
     const double* mu = reinterpret_cast<const double*>(rec + off_mean);
     const double* S = reinterpret_cast<const double*>(rec + off_sqrt);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[k][i] = pt[k];
+    for (int k = 0; k < 3; ++k) planes.p[k][d] = pt[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[3 + k][i] = mu[k];
+    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mu[k];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) planes.p[6 + 3 * r + c][i] = col_major ? S[3 * c + r] : S[3 * r + c];
+      for (int c = 0; c < 3; ++c) planes.p[6 + 3 * r + c][d] = col_major ? S[3 * c + r] : S[3 * r + c];
   }
 }
 
@@ -662,9 +662,10 @@ __global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, 
   for (int64_t i = begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < end;
        i += stride) {
     const int64_t o = i - begin;
-    for (int k = 0; k < 3; ++k) point[3 * o + k] = planes.p[k][i];
-    for (int k = 0; k < 3; ++k) mean[3 * o + k] = planes.p[3 + k][i];
-    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = planes.p[6 + k][i];
+    const int64_t d = TiledOffset(kNdtPlanes, i);
+    for (int k = 0; k < 3; ++k) point[3 * o + k] = planes.p[k][d];
+    for (int k = 0; k < 3; ++k) mean[3 * o + k] = planes.p[3 + k][d];
+    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = planes.p[6 + k][d];
   }
 }
 
@@ -672,11 +673,12 @@ __global__ void pack_reproj_kernel(const double* __restrict__ local_point,
                                    const double* __restrict__ pixel, int64_t n, PlanePtrs planes) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    planes.p[0][i] = local_point[3 * i];
-    planes.p[1][i] = local_point[3 * i + 1];
-    planes.p[2][i] = local_point[3 * i + 2];
-    planes.p[3][i] = pixel[2 * i];
-    planes.p[4][i] = pixel[2 * i + 1];
+    const int64_t d = TiledOffset(kReprojPlanes, i);
+    planes.p[0][d] = local_point[3 * i];
+    planes.p[1][d] = local_point[3 * i + 1];
+    planes.p[2][d] = local_point[3 * i + 2];
+    planes.p[3][d] = pixel[2 * i];
+    planes.p[4][d] = pixel[2 * i + 1];
   }
 }
 
@@ -825,9 +827,10 @@ __global__ void generate_ndt_kernel(const GenerateParams g) {
       }
     }
     // a point that never found a valid cell keeps S = 0 and contributes exactly nothing
-    g.planes[0][i] = lx; g.planes[1][i] = ly; g.planes[2][i] = lz;
-    for (int k = 0; k < 3; ++k) g.planes[3 + k][i] = mean[k];
-    for (int k = 0; k < 9; ++k) g.planes[6 + k][i] = S[k];
+    const int64_t d = TiledOffset(kNdtPlanes, g.dst_offset + i);
+    g.planes[0][d] = lx; g.planes[1][d] = ly; g.planes[2][d] = lz;
+    for (int k = 0; k < 3; ++k) g.planes[3 + k][d] = mean[k];
+    for (int k = 0; k < 9; ++k) g.planes[6 + k][d] = S[k];
   }
 }
 
@@ -882,7 +885,7 @@ __global__ void match_ndt_kernel(const MatchParams m) {
       }
     }
     for (int j = 0; j < m.max_neighbors; ++j) {
-      const int64_t o = static_cast<int64_t>(j) * m.n + i;
+      const int64_t o = TiledOffset(kNdtPlanes, static_cast<int64_t>(j) * m.n + i);
       const int c = best[j];
       m.planes[0][o] = lx; m.planes[1][o] = ly; m.planes[2][o] = lz;
       if (c >= 0) {
