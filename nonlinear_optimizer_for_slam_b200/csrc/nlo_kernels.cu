@@ -278,17 +278,29 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           else
             ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
         }
-        // warp tree (fixed order) -> shared
+        // Warp reduction of the NACC accumulators by recursive halving: at offset 16 each lane
+        // keeps half of the values and hands the other half to its partner, at offset 8 a
+        // quarter, ... so the butterfly costs 16+8+4+2+1 = 31 double shuffles per lane instead of
+        // 5 per value (140 for 28 values) -- SHFL issue is shared by the whole SM and was the
+        // largest fixed cost of an iteration.  Lane l ends up owning the warp total of value l.
+        // The tree is fixed, so the sum is deterministic.
+        {
+          double v[32];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-          double x = acc[k];
+          for (int k = 0; k < 32; ++k) v[k] = (k < NACC) ? acc[k] : 0.0;
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-          acc[k] = x;
-        }
-        if (lane == 0) {
+          for (int half = 16; half >= 1; half >>= 1) {
+            const bool upper = (lane & half) != 0;
 #pragma unroll
-          for (int k = 0; k < NACC; ++k) sm.warp_sums[warp][k] = acc[k];
+            for (int i = 0; i < half; ++i) {
+              if (i < NACC) {  // compile-time after unrolling: skip slots that are all padding
+                const double send = upper ? v[i] : v[i + half];
+                const double keep = upper ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+              }
+            }
+          }
+          if (lane < NACC) sm.warp_sums[warp][lane] = v[0];
         }
         if (!resident) {
           ring += my_tiles;
