@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "nonlinear_optimizer/mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_cuda.h"
+#include "nonlinear_optimizer/mahalanobis_distance_minimizer/ndt_registration_cuda.h"
 #include "nonlinear_optimizer/reprojection_error_minimizer/reprojection_error_minimizer_cuda.h"
 
 using namespace nonlinear_optimizer;
@@ -313,6 +314,38 @@ void TestMahalanobis(bool planar) {
   CHECK_NEAR(YawOf(pose), YawOf(true_pose), 5e-3);
 }
 
+// The same registration with map building, matching and the outer loop on the device.
+void TestDeviceRegistration(bool planar) {
+  using namespace mahalanobis_distance_minimizer;
+  const std::vector<Vec3> global = RoomPoints(0.02);
+  const Pose true_pose = planar ? YawPose(-0.15, 0.05, 0.0, 0.2) : YawPose(-0.2, 0.123, 0.3, 0.1);
+  const Pose true_inv = Inverse(true_pose);
+  std::vector<Vec3> local;
+  for (size_t i = 0; i < global.size(); i += 7) {
+    const double q[3] = {global[i](0), global[i](1), global[i](2)};
+    double l[3];
+    Apply(true_inv, q, l);
+    Vec3 v; v(0) = l[0]; v(1) = l[1]; v(2) = l[2];
+    local.push_back(v);
+  }
+  NdtRegistrationCuda reg;
+  reg.SetLossFunction(std::make_shared<ExponentialLossFunction>(1.0, 1.0));
+  CHECK_TRUE(reg.BuildMap(global, 1.0));
+  CHECK_TRUE(reg.SetScan(local));
+  Options options;
+  Pose pose = Pose::Identity();
+  CHECK_TRUE(reg.Register(options, &pose, planar));
+  std::cerr << "device registration: outer " << reg.last_result().outer_iterations << ", pose "
+            << PoseData(pose)[12] << " " << PoseData(pose)[13] << " " << PoseData(pose)[14] << " yaw "
+            << YawOf(pose) << ", " << reg.last_result().device_ms << " ms on the device" << std::endl;
+  const double* t = PoseData(true_pose);
+  CHECK_NEAR(PoseData(pose)[12], t[12], 2e-3);  // proper S = diag V^T: converges onto the truth
+  CHECK_NEAR(PoseData(pose)[13], t[13], 2e-3);
+  if (!planar) CHECK_NEAR(PoseData(pose)[14], t[14], 2e-3);
+  CHECK_NEAR(YawOf(pose), YawOf(true_pose), 1e-3);
+  CHECK_TRUE(reg.last_result().outer_iterations >= 2 && reg.last_result().outer_iterations <= 10);
+}
+
 }  // namespace
 
 int main(int, char**) {
@@ -322,6 +355,9 @@ int main(int, char**) {
   TestMahalanobis(false);
   std::cerr << "Start MahalanobisDistanceMinimizerCuda3DOF" << std::endl;
   TestMahalanobis(true);
+  std::cerr << "Start NdtRegistrationCuda" << std::endl;
+  TestDeviceRegistration(false);
+  TestDeviceRegistration(true);
   if (g_failures == 0) std::cerr << "ALL CXX TESTS PASSED" << std::endl;
   return g_failures == 0 ? 0 : 1;
 }
