@@ -138,7 +138,12 @@ NLO_API int nlo_ndt_download(nlo_context* ctx, const nlo_problem* problem, int64
 
 /* ---- reprojection correspondences (reprojection_error_minimizer/types.h:14-28) ---- */
 NLO_API int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
-/* intrinsics = {fx, fy, cx, cy, inv_fx, inv_fy} */
+/* `num_problems` independent PnP problems sharing one camera (the realistic multi-GPU use of the
+ * reprojection minimizer: sets are small, so registrations are batched and sharded by problem). */
+NLO_API int nlo_reproj_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts,
+                              nlo_problem** problem);
+/* intrinsics = {fx, fy, cx, cy, inv_fx, inv_fy}.  For a batched problem the arrays are the
+ * concatenation in problem order and n must equal the sum of counts. */
 NLO_API int nlo_reproj_upload(nlo_context* ctx, nlo_problem* problem, int64_t n,
                       const double* local_point, const double* pixel,
                       const double intrinsics[6]);
@@ -182,6 +187,15 @@ NLO_API int nlo_reproj_solve(nlo_context* ctx, nlo_problem* problem, const nlo_s
 NLO_API int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* problem,
                            const nlo_solve_options* options, double* poses,
                            nlo_solve_result* results);
+
+/* Planar and reprojection twins of nlo_ndt6_solve_batched (the 3-DoF one applies the reference's
+ * floor(n/4)*4 truncation to every registration). */
+NLO_API int nlo_ndt3_solve_batched(nlo_context* ctx, nlo_problem* problem,
+                           const nlo_solve_options* options, double* poses,
+                           nlo_solve_result* results);
+NLO_API int nlo_reproj_solve_batched(nlo_context* ctx, nlo_problem* problem,
+                             const nlo_solve_options* options, double* poses,
+                             nlo_solve_result* results);
 
 /* ---- next rows of the scope table: device NDT map, matcher and the outer registration loop ----
  * (the reference keeps these in its test mains, mahalanobis_distance_minimizer/tests/

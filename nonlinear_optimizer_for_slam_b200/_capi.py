@@ -58,6 +58,7 @@ _SIGNATURES = {
     "nlo_ndt_download": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int64, c_double_p,
                                         c_double_p, c_double_p]),
     "nlo_reproj_create": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),
+    "nlo_reproj_create_batched": (ctypes.c_int, [_VP, ctypes.c_int32, c_int64_p, ctypes.POINTER(_VP)]),
     "nlo_reproj_upload": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, _VP, c_double_p]),
     "nlo_problem_destroy": (ctypes.c_int, [_VP, _VP]),
     "nlo_problem_size": (ctypes.c_int64, [_VP]),
@@ -75,6 +76,10 @@ _SIGNATURES = {
                                         ctypes.POINTER(SolveResult), c_double_p]),
     "nlo_ndt6_solve_batched": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(SolveOptions), c_double_p,
                                               ctypes.POINTER(SolveResult)]),
+    "nlo_ndt3_solve_batched": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(SolveOptions), c_double_p,
+                                              ctypes.POINTER(SolveResult)]),
+    "nlo_reproj_solve_batched": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(SolveOptions), c_double_p,
+                                                ctypes.POINTER(SolveResult)]),
     "nlo_ndt_map_create": (ctypes.c_int, [_VP, c_double_p, c_int32_p, ctypes.c_double, c_double_p,
                                           c_double_p, c_uint8_p, ctypes.POINTER(_VP)]),
     "nlo_ndt_map_build": (ctypes.c_int, [_VP, ctypes.c_int64, _VP, ctypes.c_double, ctypes.c_int,

@@ -150,6 +150,20 @@ class _Problem:
                            _dp(g), ctypes.byref(cost)))
         return H, g, cost.value
 
+    def _solve_batched(self, fn, poses, options):
+        options = options or Options()
+        if not getattr(self, "batched", False):
+            raise NloError(-1, "a batched solve needs a problem created with counts=[...]")
+        B = len(self.counts)
+        poses = _f64(poses).reshape(B, 16).copy()
+        opt = options._c()
+        res = (SolveResult * B)()
+        self.ctx._check(fn(self.ctx._h, self._h, ctypes.byref(opt), _dp(poses), res))
+        return {"poses": poses,
+                "iterations": np.array([r.iterations for r in res]),
+                "final_cost": np.array([r.final_cost for r in res]),
+                "device_ms": res[0].device_ms}
+
     def _solve(self, fn, width, pose16, options, want_trace):
         pose = _f64(pose16).reshape(16).copy()
         opt = options._c()
@@ -248,27 +262,29 @@ class NdtProblem(_Problem):
         return self._solve(self._lib.nlo_ndt3_solve, TRACE3, pose16, options or Options(), trace)
 
     def solve6_batched(self, poses, options=None):
-        options = options or Options()
-        if not self.batched:
-            raise NloError(-1, "solve6_batched needs a problem created with counts=[...]")
-        B = len(self.counts)
-        poses = _f64(poses).reshape(B, 16).copy()
-        opt = options._c()
-        res = (SolveResult * B)()
-        self.ctx._check(self._lib.nlo_ndt6_solve_batched(self.ctx._h, self._h, ctypes.byref(opt),
-                                                         _dp(poses), res))
-        return {"poses": poses,
-                "iterations": np.array([r.iterations for r in res]),
-                "final_cost": np.array([r.final_cost for r in res]),
-                "device_ms": res[0].device_ms}
+        return self._solve_batched(self._lib.nlo_ndt6_solve_batched, poses, options)
+
+    def solve3_batched(self, poses, options=None):
+        return self._solve_batched(self._lib.nlo_ndt3_solve_batched, poses, options)
 
 
 class ReprojProblem(_Problem):
     """3D-2D correspondences (reprojection_error_minimizer/types.h:14-28)."""
 
-    def __init__(self, ctx, capacity):
+    def __init__(self, ctx, capacity=None, counts=None):
         super().__init__(ctx)
-        ctx._check(self._lib.nlo_reproj_create(ctx._h, int(capacity), ctypes.byref(self._h)))
+        self.batched = counts is not None
+        self.counts = None
+        if self.batched:
+            self.counts = np.ascontiguousarray(counts, dtype=np.int64)
+            ctx._check(self._lib.nlo_reproj_create_batched(
+                ctx._h, len(self.counts), self.counts.ctypes.data_as(_capi.c_int64_p),
+                ctypes.byref(self._h)))
+        else:
+            ctx._check(self._lib.nlo_reproj_create(ctx._h, int(capacity), ctypes.byref(self._h)))
+
+    def solve_batched(self, poses, options=None):
+        return self._solve_batched(self._lib.nlo_reproj_solve_batched, poses, options)
 
     def upload(self, local_point, pixel, intrinsics):
         X = _f64(local_point); px = _f64(pixel); K = _f64(intrinsics)

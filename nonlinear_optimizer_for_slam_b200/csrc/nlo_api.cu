@@ -463,6 +463,13 @@ int Solve(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* 
     int64_t max_count = 0;
     for (int64_t c : pr->counts) max_count = std::max(max_count, c);
     end_abs = max_count;
+    // per-registration ranges for this kind (3-DoF: floor(n/4)*4 of each registration)
+    std::vector<Range> ranges(pr->h_ranges);
+    if (kind == kNdt3)
+      for (int k = 0; k < B; ++k) ranges[k].end = ranges[k].begin + (pr->counts[k] / 4) * 4;
+    NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_ranges, ranges.data(), static_cast<size_t>(B) * sizeof(Range),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `ranges` is a local vector
   }
   NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_poses, poses, static_cast<size_t>(B) * 16 * sizeof(double),
                                 cudaMemcpyHostToDevice, ctx->stream));
@@ -631,6 +638,11 @@ int nlo_ndt_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t
 int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem) {
   if (capacity < 0) return Fail(ctx, NLO_EINVAL, "negative capacity");
   return CreateProblem(ctx, 1, 1, &capacity, false, problem);
+}
+
+int nlo_reproj_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts, nlo_problem** problem) {
+  if (counts == nullptr) return Fail(ctx, NLO_EINVAL, "null counts");
+  return CreateProblem(ctx, 1, num_problems, counts, true, problem);
 }
 
 int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
@@ -818,21 +830,37 @@ int nlo_ndt_download(nlo_context* ctx, const nlo_problem* pr, int64_t begin, int
 int nlo_reproj_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* local_point, const double* pixel,
                       const double intrinsics[6]) {
   if (ctx == nullptr || pr == nullptr || pr->family != 1) return Fail(ctx, NLO_EINVAL, "bad problem");
-  if (n < 0 || n > pr->counts[0] || intrinsics == nullptr || (n > 0 && (!local_point || !pixel)))
+  int64_t total = 0;
+  for (int64_t c : pr->counts) total += c;
+  if (n < 0 || (pr->batched ? (n != total) : (n > pr->counts[0])) || intrinsics == nullptr ||
+      (n > 0 && (!local_point || !pixel)))
     return Fail(ctx, NLO_EINVAL, "bad argument");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 5 * sizeof(double) + 256);
+  const size_t bytes = static_cast<size_t>(n) * 5 * sizeof(double);
+  int rc = EnsureStaging(ctx, bytes + (pr->num_problems + 1) * sizeof(int64_t) + 512);
   if (rc != NLO_OK) return rc;
   double* s_point = static_cast<double*>(ctx->staging);
   double* s_pixel = s_point + 3 * n;
+  std::vector<int64_t> prefix(pr->num_problems + 1, 0);
   if (n > 0) {
     NLO_CUDA(ctx, cudaMemcpyAsync(s_point, local_point, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NLO_CUDA(ctx, cudaMemcpyAsync(s_pixel, pixel, 2 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    NLO_CUDA(ctx, LaunchPackReproj(s_point, s_pixel, n, pr->planes, ctx->stream));
+    if (!pr->batched) {
+      NLO_CUDA(ctx, LaunchPackReproj(s_point, s_pixel, n, pr->planes, ctx->stream));
+    } else {
+      for (int k = 0; k < pr->num_problems; ++k) prefix[k + 1] = prefix[k] + pr->counts[k];
+      int64_t* d_prefix = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(ctx->staging) +
+                                                     ((bytes + 255) / 256) * 256);
+      NLO_CUDA(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * sizeof(int64_t),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+      NLO_CUDA(ctx, LaunchPackReprojBatched(s_point, s_pixel, n, d_prefix, pr->d_ranges, pr->num_problems,
+                                            pr->planes, ctx->stream));
+      NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
   }
   for (int k = 0; k < 6; ++k) pr->intrinsics[k] = intrinsics[k];
   pr->n = n;
-  pr->h_ranges[0] = Range{0, n};
+  if (!pr->batched) pr->h_ranges[0] = Range{0, n};
   DropGraphs(pr);  // intrinsics are baked into captured launches
   NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NLO_OK;
@@ -866,6 +894,15 @@ int nlo_reproj_solve(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options*
 int nlo_ndt6_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double* poses,
                            nlo_solve_result* results) {
   return Solve(ctx, pr, kNdt6, options, poses, results, nullptr, true);
+}
+
+int nlo_ndt3_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double* poses,
+                           nlo_solve_result* results) {
+  return Solve(ctx, pr, kNdt3, options, poses, results, nullptr, true);
+}
+int nlo_reproj_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_options* options, double* poses,
+                             nlo_solve_result* results) {
+  return Solve(ctx, pr, kReproj, options, poses, results, nullptr, true);
 }
 
 // ---- NDT map / scan / matcher / outer registration loop ----

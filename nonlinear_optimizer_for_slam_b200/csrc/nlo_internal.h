@@ -111,6 +111,9 @@ cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int
                             double* point, double* mean, double* sqrt_info, cudaStream_t stream);
 cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
                              double* const planes[kReprojPlanes], cudaStream_t stream);
+cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pixel, int64_t n_total,
+                                    const int64_t* src_prefix, const Range* ranges, int num_problems,
+                                    double* const planes[kReprojPlanes], cudaStream_t stream);
 
 struct GenerateParams {
   double* planes[kNdtPlanes];

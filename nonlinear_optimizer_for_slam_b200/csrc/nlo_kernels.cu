@@ -694,6 +694,25 @@ __global__ void pack_reproj_kernel(const double* __restrict__ local_point,
   }
 }
 
+__global__ void pack_reproj_batched_kernel(const double* __restrict__ local_point,
+                                           const double* __restrict__ pixel,
+                                           const int64_t* __restrict__ src_prefix,
+                                           const Range* __restrict__ ranges, PlanePtrs planes) {
+  const int b = blockIdx.y;
+  const int64_t src0 = src_prefix[b];
+  const int64_t n = src_prefix[b + 1] - src0;
+  const int64_t dst0 = ranges[b].begin;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t s = src0 + i, d = TiledOffset(kReprojPlanes, dst0 + i);
+    planes.p[0][d] = local_point[3 * s];
+    planes.p[1][d] = local_point[3 * s + 1];
+    planes.p[2][d] = local_point[3 * s + 2];
+    planes.p[3][d] = pixel[2 * s];
+    planes.p[4][d] = pixel[2 * s + 1];
+  }
+}
+
 static int GridFor(int64_t n, int threads) {
   int64_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -753,6 +772,20 @@ cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int
   if (n <= 0) return cudaSuccess;
   pack_reproj_kernel<<<GridFor(n, 256), 256, 0, stream>>>(local_point, pixel, n,
                                                           MakePlanes(planes, kReprojPlanes));
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pixel, int64_t n_total,
+                                    const int64_t* src_prefix, const Range* ranges, int num_problems,
+                                    double* const planes[kReprojPlanes], cudaStream_t stream) {
+  if (n_total <= 0) return cudaSuccess;
+  const int64_t per = (n_total + num_problems - 1) / num_problems;
+  int gx = static_cast<int>((per + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, num_problems);
+  pack_reproj_batched_kernel<<<grid, 256, 0, stream>>>(local_point, pixel, src_prefix, ranges,
+                                                       MakePlanes(planes, kReprojPlanes));
   return cudaGetLastError();
 }
 

@@ -313,3 +313,53 @@ def test_batched_generate_matches_single_generate(ctx, nlo, oracle):
         assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
         single.close()
     prob.close()
+
+
+def test_batched_3dof_and_reprojection(ctx, nlo, oracle):
+    """Batched twins of the planar and PnP minimizers: every registration equals its own oracle
+    solve (the planar one with the reference's floor(n/4)*4 truncation per registration)."""
+    rng = np.random.default_rng(21)
+    # --- 3-DoF, Huber
+    counts = [1003, 4000, 258]
+    pts, mus, Ss, refs = [], [], [], []
+    init = syn.to_pose16(syn.yaw_pose([0.01, 0.02, 0.1], 0.01))
+    for k, c in enumerate(counts):
+        T = syn.yaw_pose([rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), 0.0], rng.uniform(-0.1, 0.1))
+        p, m, s = syn.ndt_problem(c, 3000 + k, T)
+        pts.append(p); mus.append(m); Ss.append(s)
+        refs.append(oracle.ndt3_solve(p, m, s, init, 2, [1.0]))
+    ctx.set_loss(2, [1.0])
+    prob = nlo.NdtProblem(ctx, counts=[len(p) for p in pts])
+    prob.upload(np.concatenate(pts), np.concatenate(mus), np.concatenate(Ss))
+    out = prob.solve3_batched(np.tile(init, (len(counts), 1)))
+    for k in range(len(counts)):
+        pose_r, it_r, cost_r, _ = refs[k]
+        assert out["iterations"][k] == it_r
+        np.testing.assert_allclose(out["poses"][k], pose_r, rtol=0, atol=1e-6)
+        assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
+    # the same problem object still serves the 6-DoF path with full ranges
+    ctx.set_loss(1, [1.0, 1.0])
+    out6 = prob.solve6_batched(np.tile(nlo.identity_pose(), (len(counts), 1)))
+    ref6 = oracle.ndt6_solve(pts[0], mus[0], Ss[0], nlo.identity_pose(), 1, [1.0, 1.0])
+    assert out6["iterations"][0] == ref6[1]
+    np.testing.assert_allclose(out6["poses"][0], ref6[0], rtol=0, atol=1e-6)
+    prob.close()
+    # --- reprojection, Cauchy
+    counts = [630, 5000, 300]
+    Xs, pxs, refs = [], [], []
+    for k, c in enumerate(counts):
+        T = syn.yaw_pose([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(-0.3, 0.0)],
+                         rng.uniform(-0.1, 0.1))
+        X, px, K = syn.pnp_problem(c, 4000 + k, true_T=T)
+        Xs.append(X); pxs.append(px)
+        refs.append(oracle.reproj_solve(X, px, K, nlo.identity_pose(), 3, [1e-2]))
+    ctx.set_loss(3, [1e-2])
+    rp = nlo.ReprojProblem(ctx, counts=counts)
+    rp.upload(np.concatenate(Xs), np.concatenate(pxs), K)
+    out = rp.solve_batched(np.tile(nlo.identity_pose(), (len(counts), 1)))
+    for k in range(len(counts)):
+        pose_r, it_r, cost_r, _ = refs[k]
+        assert out["iterations"][k] == it_r
+        np.testing.assert_allclose(out["poses"][k], pose_r, rtol=0, atol=1e-6)
+        assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
+    rp.close()
