@@ -93,6 +93,8 @@ struct nlo_context {
   double* host_small = nullptr;  // pinned
   bool use_graph = true;
   bool use_persistent = true;
+  double l2_keep_mb = 0.0;     // NLO_L2_KEEP_MB: bytes of a re-read scan pinned in L2 (0 = off)
+  double l2_policy_min_mb = 0.0;  // only scans larger than this get an explicit policy
   int grid_small = 0;  // CTAs of the persistent path for L2-resident problems
   // communicator
   int comm_kind = kCommNone;
@@ -369,6 +371,12 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     p.mode = kModeSolve;
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
+    {
+      const double tile_mb = static_cast<double>(pr->num_planes) * kTile * sizeof(double) / 1.0e6;
+      const double scan_mb = static_cast<double>(tiles) * tile_mb;
+      if (ctx->l2_keep_mb > 0.0 && scan_mb > ctx->l2_policy_min_mb && opt.max_iterations > 1)
+        p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
+    }
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, 2 * sizeof(unsigned int), ctx->stream));
     NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream));
     return NLO_OK;
@@ -547,6 +555,15 @@ int nlo_context_create(int device, nlo_context** out) {
   ctx->grid_small = prop.multiProcessorCount;
   const char* sgenv = getenv("NLO_GRID_SMALL");
   if (sgenv != nullptr && atoi(sgenv) > 0) ctx->grid_small = atoi(sgenv);
+  // A scan that is re-read every iteration and does not fit the L2 by itself gets its first 96 MB
+  // pinned (evict_last) and the rest streamed (evict_first).  Measured on B200 (scripts/l2_sweep.sh,
+  // 3-DoF): 1 M points 23.6 -> 17.5 us / iteration, 2 M 41.3 -> 35.9, 4 M 75.4 -> 70.2; 110 MB thrashes.
+  ctx->l2_keep_mb = 96.0;
+  ctx->l2_policy_min_mb = 56.0;
+  const char* kenv = getenv("NLO_L2_KEEP_MB");
+  if (kenv != nullptr) ctx->l2_keep_mb = atof(kenv);
+  const char* menv = getenv("NLO_L2_MIN_MB");
+  if (menv != nullptr) ctx->l2_policy_min_mb = atof(menv);
   const char* denv = getenv("NLO_DEBUG_TIMES");
   if (denv != nullptr && denv[0] == '1') {
     cudaMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), 64 * 8 * sizeof(unsigned long long));

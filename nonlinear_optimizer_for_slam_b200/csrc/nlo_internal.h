@@ -82,6 +82,7 @@ struct IterParams {
   int mode;
   int use_peer;
   unsigned long long* debug_times;  // nullable: [iterations][8] globaltimer stamps of CTA 0 (profiling aid)
+  long long l2_keep_tiles;  // > 0: tiles [0, l2_keep_tiles) of the range are loaded evict_last, the rest evict_first
   int persistent;  // cooperative launch: the whole loop in one grid, grid barrier per iteration
   PeerComm peer;
 };

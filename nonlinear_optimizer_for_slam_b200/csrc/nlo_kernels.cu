@@ -64,6 +64,26 @@ __device__ __forceinline__ void BulkLoad(void* smem_dst, const void* gmem_src, u
       "l"(gmem_src), "r"(bytes), "r"(SmemAddr(bar))
       : "memory");
 }
+// Same, with an explicit L2 eviction policy (createpolicy): tiles that should stay resident in the
+// 126 MB L2 across iterations are loaded evict_last, the streamed remainder evict_first.
+__device__ __forceinline__ void BulkLoadHint(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(SmemAddr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(SmemAddr(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t PolicyEvictLast() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t PolicyEvictFirst() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void FenceBarrierInit() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -203,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       p.debug_times[static_cast<size_t>(it) * 8 + (slot)] = GlobalTimerNs();             \
   } while (0)
 
+  const uint64_t policy_keep = PolicyEvictLast(), policy_stream = PolicyEvictFirst();
   uint32_t ring = 0;  // tiles consumed so far by this CTA (keeps mbarrier phases across iterations)
   // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
   // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
@@ -230,9 +251,15 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           MbarWait(&sm.empty[s], phase ^ 1u);
           MbarExpectTx(&sm.full[s], kStageBytes);
           const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
-          // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy
-          BulkLoad(&sm.stages[s][0][0], p.planes[0] + tile * (NPLANES * kTile), kStageBytes,
-                   &sm.full[s]);
+          // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy.
+          // l2_keep_tiles > 0: the scan is re-read every iteration and is larger than what the L2
+          // keeps by itself -- pin the first tiles (evict_last), stream the rest (evict_first).
+          const double* src = p.planes[0] + tile * (NPLANES * kTile);
+          if (p.l2_keep_tiles > 0)
+            BulkLoadHint(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s],
+                         (tile - tile_lo) < p.l2_keep_tiles ? policy_keep : policy_stream);
+          else
+            BulkLoad(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s]);
         };
         const bool need_load = !resident || it == 0;
         if (tid == 0 && need_load) {
