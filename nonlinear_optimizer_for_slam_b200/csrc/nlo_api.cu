@@ -378,8 +378,15 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
     }
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, 2 * sizeof(unsigned int), ctx->stream));
-    NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream));
-    return NLO_OK;
+    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream);
+    if (ce == cudaSuccess) return NLO_OK;
+    if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+      return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
+    // the grid cannot be co-resident right now (e.g. the GPU is shared): one launch per iteration
+    cudaGetLastError();
+    p.persistent = 0;
+    p.iterations_in_kernel = 1;
+    p.l2_keep_tiles = 0;
   }
   for (int it = 0; it < opt.max_iterations; ++it) {
     if (ctx->comm_kind == kCommNccl) {

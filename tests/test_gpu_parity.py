@@ -363,3 +363,88 @@ def test_batched_3dof_and_reprojection(ctx, nlo, oracle):
         np.testing.assert_allclose(out["poses"][k], pose_r, rtol=0, atol=1e-6)
         assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
     rp.close()
+
+
+@pytest.mark.parametrize("axis,angle", [((0, 0, 1), np.pi), ((1, 0, 0), np.pi), ((0, 1, 0), 3.0),
+                                        ((1, 1, 0), np.pi), ((0.3, -0.5, 0.8), 2.9)])
+def test_initial_pose_large_rotations(ctx, nlo, oracle, axis, angle):
+    """Initial poses with trace(R) <= 0 exercise the three largest-diagonal branches of
+    Eigen's Quaterniond(Matrix3d) (..._analytic.cc:87), restated on the device in init_states."""
+    axis = np.asarray(axis, dtype=np.float64); axis /= np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+    assert np.trace(R) <= 0.0
+    pose16 = nlo.pose_from_Rt(R, [0.1, -0.2, 0.3])
+    point, mean, S = syn.random_ndt_records(3000, seed=31)
+    prob = nlo.NdtProblem(ctx, capacity=3000)
+    prob.upload(point, mean, S)
+    ctx.set_loss(1, [1.0, 1.0])
+    H, g, c = prob.assemble6(pose16)
+    Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
+    Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, Rq, [0.1, -0.2, 0.3], 1, [1.0, 1.0], long_double=True)
+    assert_sums_close(H, g, c, Hr, gr, cr)
+    res = prob.solve6(pose16, nlo.Options(max_iterations=3), trace=True)
+    ref = oracle.ndt6_solve(point, mean, S, pose16, 1, [1.0, 1.0], max_iterations=3)
+    _check_trajectory(res, ref, 36, nlo)
+    prob.close()
+
+
+def test_convergence_by_gradient_and_by_step(ctx, nlo, oracle):
+    """Both break conditions (..._analytic.cc:139-144) with the iteration count they leave behind."""
+    rng = np.random.default_rng(8)
+    point = rng.uniform(-2, 2, (4000, 3))
+    T = syn.yaw_pose([0.05, -0.03, 0.02], 0.01)
+    mean = point @ T[:3, :3].T + T[:3, 3]             # exact correspondences: cost -> 0
+    S = np.tile(np.eye(3).reshape(9), (4000, 1))
+    prob = nlo.NdtProblem(ctx, capacity=4000)
+    prob.upload(point, mean, S)
+    ctx.set_loss(0)
+    for opts in (dict(parameter_tolerance=1e-6, gradient_tolerance=1e-300),   # stops on the step norm
+                 dict(parameter_tolerance=1e-300, gradient_tolerance=1e-3),   # stops on the gradient norm
+                 dict(parameter_tolerance=1e-300, gradient_tolerance=1e-300)):  # runs to the cap
+        res = prob.solve6(nlo.identity_pose(), nlo.Options(max_iterations=25, **opts), trace=True)
+        ref = oracle.ndt6_solve(point, mean, S, nlo.identity_pose(), 0, None, max_iterations=25, **opts)
+        assert res["iterations"] == ref[1]
+        np.testing.assert_allclose(res["pose"], ref[0], rtol=0, atol=1e-6)
+    assert res["iterations"] == 25
+    Rr, tr = nlo.pose_to_Rt(res["pose"])
+    np.testing.assert_allclose(tr, T[:3, 3], atol=1e-9)
+    prob.close()
+
+
+def test_loss_edge_values(ctx, nlo, oracle):
+    """Huber exactly at / around its threshold (strict >, loss_function.h:58), exponential weights
+    that underflow to zero, Cauchy with huge residuals -- sums stay finite and match the oracle."""
+    n = 2048
+    point = np.zeros((n, 3)); mean = np.zeros((n, 3)); S = np.zeros((n, 9))
+    S[:, 0] = 1.0; S[:, 4] = 1.0; S[:, 8] = 1.0
+    r = np.linspace(0.0, 4.0, n)
+    r[100] = 2.0                                           # s == threshold^2 exactly
+    r[101] = np.nextafter(2.0, 3.0); r[102] = np.nextafter(2.0, 1.0)
+    r[-1] = 40.0; r[-2] = 1e3                              # exp(-s) underflows
+    mean[:, 0] = -r                                        # e = (r, 0, 0) at the identity pose
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.upload(point, mean, S)
+    for kind, params in ((2, [2.0]), (1, [1.0, 1.0]), (3, [0.1]), (1, [3.0, 50.0])):
+        ctx.set_loss(kind, params)
+        H, g, c = prob.assemble6(nlo.identity_pose())
+        Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, np.eye(3), np.zeros(3), kind, params, long_double=True)
+        assert np.isfinite(H).all() and np.isfinite(g).all() and np.isfinite(c)
+        assert_sums_close(H, g, c, Hr, gr, cr)
+    prob.close()
+
+
+def test_reprojection_all_points_behind_camera(ctx, nlo):
+    """Every correspondence gated out (z < 0.03): H = 0, the damped system is singular, the solve
+    reports NLO_ENUMERIC instead of returning garbage (the reference would write NaNs and return true)."""
+    X, px, K = syn.pnp_fixture()
+    X = X.copy(); X[:, 2] = -1.0
+    rp = nlo.ReprojProblem(ctx, capacity=len(X))
+    rp.upload(X, px, K)
+    ctx.set_loss(0)
+    H, g, c = rp.assemble(nlo.identity_pose())
+    assert not H.any() and not g.any() and c == 0.0
+    with pytest.raises(nlo.NloError) as e:
+        rp.solve(nlo.identity_pose())
+    assert e.value.code == -5
+    rp.close()
