@@ -16,7 +16,6 @@
 #include <cstring>
 #include <map>
 #include <string>
-#include <tuple>
 #include <vector>
 
 #include "../../include/nlo_cuda.h"
@@ -132,7 +131,6 @@ struct nlo_problem {
   double* d_trace = nullptr;
   size_t trace_doubles = 0;
   double intrinsics[6] = {0, 0, 0, 0, 0, 0};
-  int grid_x = 1;
   std::map<std::array<int64_t, 10>, cudaGraphExec_t> graphs;
 };
 
@@ -228,7 +226,6 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   // tile-interleaved layout: plane k of tile 0 starts at k * 256 (nlo_internal.h TiledOffset)
   for (int k = 0; k < pr->num_planes; ++k) pr->planes[k] = pr->plane_block + static_cast<size_t>(k) * kTile;
   const int slots = num_problems + 1;
-  pr->grid_x = batched ? 1 : ctx->grid_single;
   NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
   NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
   NLO_CUDA_P(cudaMalloc(&pr->d_partials,
