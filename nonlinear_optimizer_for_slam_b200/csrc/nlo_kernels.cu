@@ -1,15 +1,22 @@
 // nlo_kernels.cu -- sm_100a kernels of the hot path.
 //
-// gn_iteration_kernel<KIND, LOSS>: one Gauss-Newton / damped-LM iteration (or, for a registration
-// that fits one CTA, the whole loop) of one or many registrations:
+// gn_iteration_kernel<KIND, LOSS>: the device-resident Gauss-Newton / damped-LM loop (or a single
+// iteration of it) of one or many registrations:
 //
-//   HBM SoA planes --cp.async.bulk (TMA 1-D), mbarrier full/empty ring--> shared memory stages
-//     --> 8 consumer warps: residual, analytic Jacobian terms, robust-loss weight, 28 (10) fp64
+//   HBM tiles (tile-interleaved SoA, one contiguous 30 KB run per 256 correspondences)
+//     --cp.async.bulk (TMA 1-D, one copy per tile, L2 eviction hint), mbarrier full/empty ring-->
+//   shared-memory stages (resident across iterations when the CTA's share fits the ring)
+//     --> 8 warps: residual, analytic Jacobian terms, device-inlined robust loss, 28 (10) fp64
 //         register accumulators per thread
-//     --> warp shuffle -> shared -> per-CTA partial -> (last CTA by ticket) fixed-order fp64 sum
-//     --> [peer-memory all-reduce over NVLink when sharded across GPUs]
-//     --> one thread: rotate to the canonical H|g, damp, 6x6 / 3x3 solve, pose update,
-//         convergence tests, lambda schedule, trace row; state stays in HBM for the next launch.
+//     --> recursive-halving warp reduction -> shared -> per-CTA partial (HBM/L2)
+//     --> leader CTA: fixed-order fp64 sum of the partials, rotation to the canonical H|g,
+//         [LL-format peer-memory all-reduce over NVLink when the scan is sharded across GPUs],
+//         damped 6x6 LDL^T / 3x3 solve, pose update, convergence tests, lambda schedule, trace row
+//     --> new state published to the other CTAs (persistent grid) or left in HBM (next launch).
+//
+// Launch shapes (chosen in nlo_api.cu): persistent cooperative grid with the whole loop inside,
+// one CTA per registration with the whole loop inside (batched), or one launch per iteration
+// with a last-CTA-by-ticket finaliser (NCCL flavour, plain assemble calls).
 //
 // Replaces the per-iteration loops of (paths relative to /root/reference/nonlinear_optimizer/)
 //   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_analytic.cc:92-149
