@@ -126,11 +126,12 @@ def cpu_reference_rates(sample_points, min_seconds, threads):
     import nlo_oracle_py as oracle
     from nonlinear_optimizer_for_slam_b200 import synthetic as syn
     oracle.build()
+    native = oracle.use_native_build()   # -march=native on this host, as the reference builds
     point, mean, S = syn.ndt_problem(sample_points, SEED, syn.CFG1_TRUE)
     n = len(point)
     R = np.eye(3); t = np.zeros(3)
     planes = oracle.simd_pack(point, mean, S)
-    out = {}
+    out = {"native_build": native}
     for name, fn in (
             ("scalar_f64", lambda: oracle.ndt6_assemble_threads(point, mean, S, R, t, 1, [1.0, 1.0], threads)),
             ("avx2_f32", lambda: oracle.simd_ndt6_assemble(planes, n, R, t, 1, [1.0, 1.0], threads))):
@@ -156,6 +157,7 @@ def run_reference(args):
     import nlo_oracle_py as oracle
     from nonlinear_optimizer_for_slam_b200 import synthetic as syn
     oracle.build()
+    native = oracle.use_native_build()   # -march=native on this host, as the reference builds
     point, mean, S = syn.ndt_problem(sample, SEED, syn.CFG1_TRUE)
     n = len(point)
     planes = oracle.simd_pack(point, mean, S)
@@ -173,7 +175,8 @@ def run_reference(args):
     oracle.ndt6_assemble_threads(point, mean, S, R, t, 1, [1.0, 1.0], threads)
     scalar = n / (time.perf_counter() - ts) / 1e9
     sample_txt = ("%d correspondences of cfg4 (same generator, seed %d) per step, float AVX2+FMA SoA "
-                  "assembly (SolveFloatIntrinsicAligned restated) on %d std::threads" % (n, SEED, threads))
+                  "assembly (SolveFloatIntrinsicAligned restated) on %d std::threads, %s"
+                  % (n, SEED, threads, "-O2 -march=native" if native else "-O2 -mavx2 -mfma"))
     line = {
         "impl": "reference", "metric": "NDT 6-DoF assembly Gpoints/s", "value": value,
         "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -305,7 +308,8 @@ def run_cuda(args):
         cpu = {"value": rates["avx2_f32"]["gpoints_s"], "unit": "Gpoints/s", "cores": threads,
                "kind": "port",
                "sample": "%d correspondences of cfg4, >= 4 s per variant; value = float AVX2+FMA SoA "
-                         "path (fastest reference variant) on all threads" % n_s,
+                         "path (fastest reference variant) on all threads, %s"
+                         % (n_s, "-O2 -march=native" if rates["native_build"] else "-O2 -mavx2 -mfma"),
                "scalar_f64_gpoints_s": rates["scalar_f64"]["gpoints_s"]}
 
     if rank == 0:

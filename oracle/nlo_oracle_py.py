@@ -33,6 +33,27 @@ def build(force=False):
     return _LIB_PATH
 
 
+def use_native_build():
+    """Rebuild the library with -march=native on THIS machine (the reference's own flags,
+    CMakeLists.txt:10-13) and load that copy.  For the CPU timing baseline only: the parity tests
+    keep the portable, FMA-free build.  Returns True on success."""
+    global _lib
+    native = os.path.join(_HERE, "_native", "libnlo_oracle.so")
+    try:
+        if os.path.exists(native):
+            os.remove(native)   # never load a copy that was built for another machine's -march
+        subprocess.run(["make", "-C", _HERE, "native"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        candidate = ctypes.CDLL(native)
+    except Exception:
+        return False
+    candidate.nlo_oracle_voxel_key.restype = ctypes.c_uint64
+    candidate.nlo_oracle_pnp_reference_points.restype = ctypes.c_int64
+    candidate.nlo_oracle_room_points.restype = ctypes.c_int64
+    _lib = candidate
+    return True
+
+
 _lib = None
 
 
