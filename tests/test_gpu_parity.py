@@ -448,3 +448,38 @@ def test_reprojection_all_points_behind_camera(ctx, nlo):
         rp.solve(nlo.identity_pose())
     assert e.value.code == -5
     rp.close()
+
+
+def test_point_to_plane_is_a_rank_one_ndt_record(ctx, nlo):
+    """the point-to-plane residual r = n^T (R p + t - q) of the reference's unfinished
+    pose_optimizer/cost_functors.h is the NDT residual with sqrt_information = [n^T; 0; 0] and
+    mean = q, so the same kernel assembles it.  Checked against normal equations built in numpy
+    straight from the point-to-plane definition."""
+    rng = np.random.default_rng(12)
+    n = 5000
+    p = rng.uniform(-2, 2, (n, 3))
+    normal = rng.normal(size=(n, 3)); normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    T = syn.yaw_pose([0.04, -0.02, 0.03], 0.02)
+    q = p @ T[:3, :3].T + T[:3, 3] + rng.normal(0, 0.01, (n, 3))
+    S = np.zeros((n, 9)); S[:, 0:3] = normal
+    prob = nlo.NdtProblem(ctx, capacity=n)
+    prob.upload(p, q, S)
+    ctx.set_loss(0)
+    R0 = syn.random_rotation(rng, 0.05); t0 = np.array([0.01, 0.0, -0.01])
+    Rq = R0  # already a rotation; the quaternion round trip only re-normalises it
+    H, g, c = prob.assemble6(nlo.pose_from_Rt(R0, t0))
+    r = np.einsum("ni,ni->n", normal, p @ Rq.T + t0 - q)
+    J = np.zeros((n, 6))
+    J[:, :3] = normal
+    skew = np.zeros((n, 3, 3))
+    skew[:, 0, 1] = -p[:, 2]; skew[:, 0, 2] = p[:, 1]; skew[:, 1, 0] = p[:, 2]
+    skew[:, 1, 2] = -p[:, 0]; skew[:, 2, 0] = -p[:, 1]; skew[:, 2, 1] = p[:, 0]
+    J[:, 3:] = -np.einsum("ni,nij->nj", normal @ Rq, skew)
+    Href = J.T @ J
+    iu = np.triu_indices(6)
+    assert_sums_close(H, g, c, Href[iu], J.T @ r, float(r @ r), tol=1e-9)
+    res = prob.solve6(nlo.identity_pose(), nlo.Options(max_iterations=60))
+    Rr, tr = nlo.pose_to_Rt(res["pose"])
+    np.testing.assert_allclose(tr, T[:3, 3], atol=2e-3)     # point-to-plane ICP recovers the motion
+    assert rotation_angle(Rr, T[:3, :3]) < 2e-3
+    prob.close()
