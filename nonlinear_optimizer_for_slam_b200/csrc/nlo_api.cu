@@ -105,6 +105,8 @@ struct nlo_context {
   PeerComm peer{};
   unsigned long long* d_peer_seq = nullptr;
   int* d_peer_error = nullptr;
+  nlo_problem* reg_workspace = nullptr;  // correspondences of nlo_ndt_register: kept across scans,
+  int64_t reg_workspace_capacity = 0;    // grown on demand (no per-frame allocation)
   unsigned long long* d_debug_times = nullptr;  // NLO_DEBUG_TIMES=1: [64][8] stamps of the last loop
   int generation = 0;  // bumped whenever cached graphs become stale (loss / comm change)
 };
@@ -148,8 +150,6 @@ struct nlo_scan {
   int64_t n = 0;
   double* block = nullptr;
   double* planes[3] = {nullptr, nullptr, nullptr};
-  nlo_problem* workspace = nullptr;  // correspondences of nlo_ndt_register, grown on demand
-  int64_t workspace_capacity = 0;
   unsigned long long* d_matched = nullptr;
 };
 
@@ -591,6 +591,8 @@ int nlo_context_destroy(nlo_context* ctx) {
   if (ctx == nullptr) return NLO_OK;
   cudaSetDevice(ctx->device);
   nlo_comm_destroy(ctx);
+  if (ctx->reg_workspace) nlo_problem_destroy(ctx, ctx->reg_workspace);
+  ctx->reg_workspace = nullptr;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->d_debug_times) cudaFree(ctx->d_debug_times);
@@ -1117,11 +1119,12 @@ int nlo_scan_create(nlo_context* ctx, int64_t n, const double* points_xyz, nlo_s
   nlo_scan* sc = new nlo_scan();
   sc->n = n;
   const int64_t cap = std::max<int64_t>(n, 1);
-  if (cudaMalloc(&sc->block, cap * 3 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&sc->d_matched, sizeof(unsigned long long)) != cudaSuccess) {
+  // one allocation: three planes + the matched-correspondence counter behind them
+  if (cudaMalloc(&sc->block, (cap * 3 + 8) * sizeof(double)) != cudaSuccess) {
     nlo_scan_destroy(ctx, sc);
     return Fail(ctx, NLO_ENOMEM, "cudaMalloc(scan) failed");
   }
+  sc->d_matched = reinterpret_cast<unsigned long long*>(sc->block + cap * 3);
   for (int k = 0; k < 3; ++k) sc->planes[k] = sc->block + static_cast<size_t>(k) * cap;
   if (n > 0) {
     int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 3 * sizeof(double));
@@ -1142,9 +1145,7 @@ int nlo_scan_create(nlo_context* ctx, int64_t n, const double* points_xyz, nlo_s
 int nlo_scan_destroy(nlo_context* ctx, nlo_scan* scan) {
   if (scan == nullptr) return NLO_OK;
   if (ctx != nullptr) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  if (scan->workspace) nlo_problem_destroy(ctx, scan->workspace);
   cudaFree(scan->block);
-  cudaFree(scan->d_matched);
   delete scan;
   return NLO_OK;
 }
@@ -1176,14 +1177,15 @@ int nlo_ndt_register(nlo_context* ctx, const nlo_scan* scan_in, const nlo_ndt_ma
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   nlo_scan* scan = const_cast<nlo_scan*>(scan_in);
   const int64_t need = static_cast<int64_t>(max_neighbors) * scan->n;
-  if (scan->workspace == nullptr || scan->workspace_capacity < need) {
-    if (scan->workspace) nlo_problem_destroy(ctx, scan->workspace);
-    scan->workspace = nullptr;
-    int rc = nlo_ndt_create(ctx, std::max<int64_t>(need, 1), &scan->workspace);
+  if (ctx->reg_workspace == nullptr || ctx->reg_workspace_capacity < need) {
+    if (ctx->reg_workspace) nlo_problem_destroy(ctx, ctx->reg_workspace);
+    ctx->reg_workspace = nullptr;
+    const int64_t cap = std::max<int64_t>(need + need / 2, 4096);
+    int rc = nlo_ndt_create(ctx, cap, &ctx->reg_workspace);
     if (rc != NLO_OK) return rc;
-    scan->workspace_capacity = std::max<int64_t>(need, 1);
+    ctx->reg_workspace_capacity = cap;
   }
-  nlo_problem* pr = scan->workspace;
+  nlo_problem* pr = ctx->reg_workspace;
   memset(result, 0, sizeof(*result));
   cudaEvent_t e0, e1;
   NLO_CUDA(ctx, cudaEventCreate(&e0));
