@@ -632,6 +632,7 @@ int nlo_set_loss(nlo_context* ctx, int kind, const double params[2]) {
       break;
     case NLO_LOSS_CAUCHY:
       if (params == nullptr || !(p0 > 0.0)) return Fail(ctx, NLO_EINVAL, "c should be larger than zero");
+      p1 = 1.0 / (p0 * p0);  // the kernels multiply by 1 / c^2 instead of dividing per correspondence
       break;
     default: return Fail(ctx, NLO_EINVAL, "unknown loss kind");
   }
