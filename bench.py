@@ -28,6 +28,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BYTES_PER_CORR = 120  # 15 fp64 scalars: point 3 + mean 3 + sqrt_information 9
 TOTAL_POINTS = 64 * 1024 * 1024
