@@ -28,8 +28,24 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class StdoutGuard:
+    """stdout must carry exactly ONE JSON line, but native libraries (NCCL's version banner, ...)
+    write to file descriptor 1 behind Python's back.  For the duration of the run fd 1 is pointed
+    at stderr; emit() writes the JSON line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
 
 BYTES_PER_CORR = 120  # 15 fp64 scalars: point 3 + mean 3 + sqrt_information 9 (SURVEY.md 8d)
 TOTAL_POINTS = 64 * 1024 * 1024
@@ -192,7 +208,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    GUARD.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------ CUDA arm
@@ -344,7 +360,7 @@ def run_cuda(args):
             "clocks": clocks,
         }
         line.update(extra)
-        print(json.dumps(line))
+        GUARD.emit(json.dumps(line))
     prob.close()
     if dist is not None:
         barrier()
@@ -488,6 +504,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
+    global GUARD
+    GUARD = StdoutGuard()
     if args.impl == "reference":
         run_reference(args)
     else:
