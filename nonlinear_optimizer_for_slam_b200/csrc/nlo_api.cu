@@ -126,7 +126,7 @@ struct nlo_problem {
   State* d_states = nullptr;  // [num_problems + 1]
   double* d_partials = nullptr;
   unsigned int* d_tickets = nullptr;  // [num_problems + 1]
-  unsigned int* d_barrier = nullptr;  // [num_problems + 1]
+  unsigned long long* d_sync = nullptr;  // [num_problems + 1][kSyncStride] persistent-path counter + LL state
   double* d_sums = nullptr;           // [(num_problems + 1) * 32]
   double* d_poses = nullptr;          // [(num_problems + 1) * 16]
   double* d_results = nullptr;        // [(num_problems + 1) * 4]
@@ -230,8 +230,8 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
   NLO_CUDA_P(cudaMalloc(&pr->d_partials,
                         2 * static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double)));
-  NLO_CUDA_P(cudaMalloc(&pr->d_barrier, 2 * slots * sizeof(unsigned int)));
-  NLO_CUDA_P(cudaMemsetAsync(pr->d_barrier, 0, 2 * slots * sizeof(unsigned int), ctx->stream));
+  NLO_CUDA_P(cudaMalloc(&pr->d_sync, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long)));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_tickets, 0, slots * sizeof(unsigned int), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
@@ -259,7 +259,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   memset(&p, 0, sizeof(p));
   for (int k = 0; k < pr->num_planes; ++k) p.planes[k] = pr->planes[k];
   p.partials = pr->d_partials;
-  p.barrier = pr->d_barrier;
+  p.sync_words = pr->d_sync;
   p.loss_p0 = ctx->loss_params[0];
   p.loss_p1 = ctx->loss_params[1];
   for (int k = 0; k < 6; ++k) p.intrinsics[k] = pr->intrinsics[k];
@@ -374,7 +374,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
       if (ctx->l2_keep_mb > 0.0 && scan_mb > ctx->l2_policy_min_mb && opt.max_iterations > 1)
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
     }
-    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_barrier, 0, 2 * sizeof(unsigned int), ctx->stream));
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, kSyncStride * sizeof(unsigned long long), ctx->stream));
     const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream);
     if (ce == cudaSuccess) return NLO_OK;
     if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
@@ -681,7 +681,7 @@ int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
   cudaFree(pr->d_states);
   cudaFree(pr->d_partials);
   cudaFree(pr->d_tickets);
-  cudaFree(pr->d_barrier);
+  cudaFree(pr->d_sync);
   cudaFree(pr->d_sums);
   cudaFree(pr->d_poses);
   cudaFree(pr->d_results);

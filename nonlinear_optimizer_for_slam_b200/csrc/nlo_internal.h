@@ -17,6 +17,7 @@ constexpr int kReprojPlanes = 5;      // X Y Z | u v
 constexpr int kAcc6 = 28;             // 21 H + 6 g + cost
 constexpr int kAcc3 = 10;             // 6 H + 3 g + cost
 constexpr int kMaxRanks = 8;
+constexpr int kSyncStride = 8 + 64;    // 8-byte words per registration of IterParams::sync_words
 constexpr int kPeerWords = 64;        // 8-byte words per (parity, source rank) slot of the peer exchange
 
 // Per-registration optimisation state, resident in HBM for the whole solve.
@@ -71,7 +72,8 @@ struct IterParams {
   State* states;        // [num_problems]
   double* partials;     // [2 parities][num_problems][grid.x][nacc]
   unsigned int* tickets;  // [num_problems] last-CTA election of the one-iteration-per-launch path
-  unsigned int* barrier;  // [num_problems][2] persistent path: arrival counter | published state sequence (0 at launch)
+  unsigned long long* sync_words;  // persistent path, per registration kSyncStride words (zeroed at launch):
+                                   // word 0 = arrival counter (u32), words 8.. = the published state as LL words
   double* sums;           // [num_problems][32] canonical H|g|cost (out for assemble, in for step-only)
   double* trace;          // nullable: [num_problems][max_iterations][trace_width]
   double loss_p0, loss_p1;

@@ -125,6 +125,7 @@ struct SmemLayout {
   State state;                 // CTA-local copy of the registration state
   uint64_t full[T::kStages];
   uint64_t empty[T::kStages];
+  unsigned int halves[kPeerWords];  // payload halves of the published state (LL words)
   int flag;
 };
 
@@ -369,44 +370,60 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
         }
         if (p.persistent) {
           // Persistent grid: every CTA arrives on a counter; CTA 0 (the leader) waits for all
-          // partials, reduces them, [all-reduces over NVLink], steps and PUBLISHES the new state
-          // with a sequence word; the other CTAs wait for that word and reload the 160-byte state.
-          unsigned int* counter = p.barrier + 2 * problem;
-          unsigned int* state_seq = counter + 1;
+          // partials, reduces them, [all-reduces over NVLink], steps and PUBLISHES the new 160-byte
+          // state as 40 "LL" words (32 payload bits + the iteration number in one 8-byte store, so
+          // a word is valid the moment its number matches: no fence, no separate flag); the other
+          // CTAs poll those words -- one L2 round trip after the leader's stores -- and rebuild
+          // the state.
+          constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
+          unsigned int* counter = reinterpret_cast<unsigned int*>(p.sync_words + problem * kSyncStride);
+          unsigned long long* ll_state = p.sync_words + problem * kSyncStride + 8;
           const unsigned int want = static_cast<unsigned int>(it) + 1u;
           __syncthreads();
           if (tid == 0) {
             __threadfence();  // releases this CTA's partial (cumulative over the bar.sync above)
             atomicAdd(counter, 1u);
             sm.flag = 1;
-            const unsigned long long start = GlobalTimerNs();
-            if (blockIdx.x == 0) {
+          }
+          const unsigned long long start = GlobalTimerNs();
+          if (blockIdx.x == 0) {
+            if (tid == 0) {
               while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
                 if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
-            } else {
-              while (*reinterpret_cast<volatile unsigned int*>(state_seq) < want)
-                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
-            }
-            __threadfence();
-          }
-          __syncthreads();
-          if (sm.flag == 0) {  // a CTA went missing (cannot happen under a cooperative launch)
-            if (tid == 0) {
-              st.status = 2;
-              st.done = 1;
-              if (blockIdx.x == 0) {
-                *st_global = st;
-                __threadfence();
-                *reinterpret_cast<volatile unsigned int*>(state_seq) = want;
-              }
+              __threadfence();
             }
             __syncthreads();
-            break;
-          }
-          if (blockIdx.x != 0) {
-            if (tid < static_cast<int>(sizeof(State) / sizeof(double)))
-              reinterpret_cast<double*>(&st)[tid] =
-                  __ldcg(reinterpret_cast<const double*>(st_global) + tid);
+            if (sm.flag == 0) {  // a CTA went missing (cannot happen under a cooperative launch)
+              if (tid == 0) { st.status = 2; st.done = 1; *st_global = st; }
+              __syncthreads();
+              if (tid < kStateWords) {  // still publish, so that the other CTAs leave as well
+                const unsigned long long bits = static_cast<unsigned long long>(
+                    __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
+                __stcg(ll_state + tid, (static_cast<unsigned long long>(want) << 32) |
+                                           ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
+              }
+              break;
+            }
+          } else {
+            __syncthreads();  // sm.flag = 1 visible
+            if (tid < kStateWords) {
+              const volatile unsigned long long* src = ll_state + tid;
+              unsigned long long w = *src;
+              while (static_cast<unsigned int>(w >> 32) != want) {
+                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
+                w = *src;
+              }
+              sm.halves[tid] = static_cast<unsigned int>(w);
+            }
+            __syncthreads();
+            if (sm.flag == 0) {  // the leader went missing
+              if (tid == 0) { st.status = 2; st.done = 1; }
+              __syncthreads();
+              break;
+            }
+            if (tid < kStateWords / 2)
+              reinterpret_cast<double*>(&st)[tid] = __longlong_as_double(static_cast<long long>(
+                  (static_cast<unsigned long long>(sm.halves[2 * tid + 1]) << 32) | sm.halves[2 * tid]));
             __syncthreads();
             continue;
           }
@@ -482,17 +499,20 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           Step6(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
                 trace_row);
       }
-      if (lane == 0 && writer) {
-        *st_global = st;
-        if (p.persistent && grid_x > 1) {  // publish to the follower CTAs
-          __threadfence();
-          *reinterpret_cast<volatile unsigned int*>(p.barrier + 2 * problem + 1) =
-              static_cast<unsigned int>(it) + 1u;
-        }
-      }
+      if (lane == 0 && writer) *st_global = st;
     }
     NLO_STAMP(5);
     __syncthreads();
+    if (p.persistent && grid_x > 1 && p.mode == kModeSolve) {  // leader: publish the new state
+      constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
+      if (tid < kStateWords) {
+        const unsigned long long bits = static_cast<unsigned long long>(
+            __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
+        __stcg(p.sync_words + problem * kSyncStride + 8 + tid,
+               (static_cast<unsigned long long>(it + 1) << 32) |
+                   ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
+      }
+    }
     NLO_STAMP(6);
   }
 #undef NLO_STAMP
