@@ -18,7 +18,8 @@
  *     COLUMN-major order (the memory of Eigen::Isometry3d, types.h:31).
  *   - host arrays use the reference's record order: point[3n] xyz interleaved, mean[3n],
  *     sqrt_info[9n] ROW-major 3x3 per correspondence (S(i,j) at 9k+3i+j), local_point[3n],
- *     pixel[2n].  On the device they are repacked into SoA planes (DESIGN.md "HBM layout").
+ *     pixel[2n].  On the device they are repacked into a tile-interleaved SoA layout (DESIGN.md
+ *     section 2): 256 correspondences per tile, the 15 (5) planes of a tile back to back.
  *   - H is the packed upper triangle in row-major order: 6-DoF 21 values
  *     (0,0),(0,1)..(0,5),(1,1)..(5,5); 3-DoF 6 values.  g is J^T W r (6 or 3).
  *   - a context owns one CUDA device + one stream; calls on one context are serialised by the
