@@ -353,6 +353,24 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
   const int64_t tiles = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
   const bool in_cta_loop =
       (ctx->comm_kind == kCommNone) && (pr->batched || tiles <= kInCtaTiles);
+  if (pr->batched && ctx->comm_kind == kCommNone && ctx->use_persistent && tiles > kInCtaTiles &&
+      2 * num_problems <= ctx->grid_single) {
+    // A small batch: one CTA per registration would leave most SMs idle, so every registration
+    // gets G = (2 x SMs) / B CTAs of ONE persistent cooperative grid (gridDim.y = registrations),
+    // each with its own leader CTA, arrival counter and published state.
+    const int gx = static_cast<int>(std::min<int64_t>(ctx->grid_single / num_problems, tiles));
+    IterParams q = p;
+    q.mode = kModeSolve;
+    q.persistent = 1;
+    q.iterations_in_kernel = opt.max_iterations;
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(num_problems) * kSyncStride * sizeof(unsigned long long),
+                                  ctx->stream));
+    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, q, gx, num_problems, ctx->stream);
+    if (ce == cudaSuccess) return NLO_OK;
+    if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+      return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
+    cudaGetLastError();  // not co-resident right now: fall through to one CTA per registration
+  }
   if (in_cta_loop) {
     // whole loop inside one CTA per registration: a single launch
     p.mode = kModeSolve;

@@ -483,3 +483,33 @@ def test_point_to_plane_is_a_rank_one_ndt_record(ctx, nlo):
     np.testing.assert_allclose(tr, T[:3, 3], atol=2e-3)     # point-to-plane ICP recovers the motion
     assert rotation_angle(Rr, T[:3, :3]) < 2e-3
     prob.close()
+
+
+def test_small_batch_uses_many_ctas_per_registration(ctx, nlo, oracle):
+    """A batch with fewer registrations than SMs runs as one persistent grid with several CTAs per
+    registration (own leader, counter and published state each); results must equal the oracle and
+    the one-CTA-per-registration path (a batch too large for that shape)."""
+    rng = np.random.default_rng(17)
+    counts = [30000, 5000, 12345, 800, 20001]
+    pts, mus, Ss, refs = [], [], [], []
+    ctx.set_loss(1, [1.0, 1.0])
+    for k, c in enumerate(counts):
+        T = syn.yaw_pose(rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.1, 0.1))
+        p, m, s = syn.ndt_problem(c, 6000 + k, T)
+        pts.append(p); mus.append(m); Ss.append(s)
+        refs.append(oracle.ndt6_solve(p, m, s, nlo.identity_pose(), 1, [1.0, 1.0]))
+    prob = nlo.NdtProblem(ctx, counts=[len(p) for p in pts])
+    prob.upload(np.concatenate(pts), np.concatenate(mus), np.concatenate(Ss))
+    out = prob.solve6_batched(np.tile(nlo.identity_pose(), (len(counts), 1)))
+    for k in range(len(counts)):
+        pose_r, it_r, cost_r, _ = refs[k]
+        assert out["iterations"][k] == it_r
+        np.testing.assert_allclose(out["poses"][k], pose_r, rtol=0, atol=1e-6)
+        assert abs(out["final_cost"][k] - cost_r) <= TOL * abs(cost_r)
+    # 3-DoF twin through the same shape
+    ctx.set_loss(2, [1.0])
+    out3 = prob.solve3_batched(np.tile(nlo.identity_pose(), (len(counts), 1)))
+    ref3 = oracle.ndt3_solve(pts[0], mus[0], Ss[0], nlo.identity_pose(), 2, [1.0])
+    assert out3["iterations"][0] == ref3[1]
+    np.testing.assert_allclose(out3["poses"][0], ref3[0], rtol=0, atol=1e-6)
+    prob.close()
