@@ -75,18 +75,48 @@ def ncu_traffic_per_launch(points, iterations_in_launch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML polled every ~2 ms
+    from a thread (the region can be as short as 20 ms); nvidia-smi -lms as a fallback."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
+        self.samples = []   # (timestamp, sm_mhz, reasons bitmask or None)
         self.rows = []
         self.proc = None
         self.thread = None
+        self.stop_flag = False
+        self.max_mhz = None
+        self.nvml = None
+
+    def _nvml_loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
@@ -95,6 +125,7 @@ class ClockSampler:
         except Exception:
             self.proc = None
             return
+
         def pump():
             for line in self.proc.stdout:
                 self.rows.append((time.perf_counter(), line.strip()))
@@ -102,6 +133,22 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self, t0=None, t1=None):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            nv = self.nvml
+            inside = [x for x in self.samples if t0 is None or t0 <= x[0] <= t1] or self.samples
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, v in names.items() if bits & v)
+            sm = [x[1] for x in inside]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms period, inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -127,7 +174,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def dist_env():
