@@ -182,15 +182,22 @@ class _Problem:
 class NdtProblem(_Problem):
     """NDT / Mahalanobis correspondences (mahalanobis_distance_minimizer/types.h:11-26)."""
 
-    def __init__(self, ctx, capacity=None, counts=None):
+    def __init__(self, ctx, capacity=None, counts=None, storage="f64"):
+        """storage="f32": correspondences stored as float on the device (fp64 math), the opt-in
+        throughput mode; the default "f64" is the parity mode."""
         super().__init__(ctx)
         self.batched = counts is not None
         self.counts = None
+        self.storage = storage
         if self.batched:
+            if storage != "f64":
+                raise NloError(-1, "batched problems are fp64 only")
             self.counts = np.ascontiguousarray(counts, dtype=np.int64)
             ctx._check(self._lib.nlo_ndt_create_batched(
                 ctx._h, len(self.counts), self.counts.ctypes.data_as(_capi.c_int64_p),
                 ctypes.byref(self._h)))
+        elif storage == "f32":
+            ctx._check(self._lib.nlo_ndt_create_f32(ctx._h, int(capacity), ctypes.byref(self._h)))
         else:
             ctx._check(self._lib.nlo_ndt_create(ctx._h, int(capacity), ctypes.byref(self._h)))
 

@@ -118,6 +118,7 @@ struct nlo_problem {
   int64_t n = 0;
   int num_problems = 1;
   bool batched = false;
+  bool f32 = false;  // planes stored as float (NDT, single problem only): fp32 storage, fp64 math
   double* plane_block = nullptr;
   double* planes[kNdtPlanes] = {nullptr};
   std::vector<Range> h_ranges;
@@ -190,7 +191,7 @@ void DropGraphs(nlo_problem* pr) {
 int64_t PadToTile(int64_t n) { return ((n + kTile - 1) / kTile) * kTile; }
 
 int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t* counts,
-                  bool batched, nlo_problem** out) {
+                  bool batched, nlo_problem** out, bool f32 = false) {
   if (ctx == nullptr || out == nullptr || num_problems < 1) return Fail(ctx, NLO_EINVAL, "bad argument");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   nlo_problem* pr = new nlo_problem();
@@ -198,6 +199,7 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   pr->num_planes = (family == 0) ? kNdtPlanes : kReprojPlanes;
   pr->num_problems = num_problems;
   pr->batched = batched;
+  pr->f32 = f32;
   int64_t cursor = 0;
   for (int k = 0; k < num_problems; ++k) {
     if (counts[k] < 0) {
@@ -209,7 +211,8 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
     cursor += std::max<int64_t>(PadToTile(counts[k]), kTile);
   }
   pr->capacity = cursor;
-  const size_t plane_bytes = static_cast<size_t>(pr->capacity) * sizeof(double);
+  const size_t elem = f32 ? sizeof(float) : sizeof(double);
+  const size_t plane_bytes = static_cast<size_t>(pr->capacity) * elem;
   auto fail_free = [&](int code, const std::string& msg) {
     nlo_problem_destroy(ctx, pr);
     return Fail(ctx, code, msg);
@@ -224,7 +227,9 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA_P(cudaMalloc(&pr->plane_block, plane_bytes * pr->num_planes));
   NLO_CUDA_P(cudaMemsetAsync(pr->plane_block, 0, plane_bytes * pr->num_planes, ctx->stream));
   // tile-interleaved layout: plane k of tile 0 starts at k * 256 (nlo_internal.h TiledOffset)
-  for (int k = 0; k < pr->num_planes; ++k) pr->planes[k] = pr->plane_block + static_cast<size_t>(k) * kTile;
+  for (int k = 0; k < pr->num_planes; ++k)
+    pr->planes[k] = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(pr->plane_block) +
+                                              static_cast<size_t>(k) * kTile * elem);
   const int slots = num_problems + 1;
   NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
   NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
@@ -267,6 +272,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   p.gradient_tolerance = 1e-6;
   p.max_iterations = 1;
   p.iterations_in_kernel = 1;
+  p.f32 = pr->f32 ? 1 : 0;
   p.debug_times = ctx->d_debug_times;
   p.use_peer = (ctx->comm_kind == kCommPeer) ? 1 : 0;
   p.peer = ctx->peer;
@@ -387,7 +393,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
     {
-      const double tile_mb = static_cast<double>(pr->num_planes) * kTile * sizeof(double) / 1.0e6;
+      const double tile_mb = static_cast<double>(pr->num_planes) * kTile * (pr->f32 ? 4.0 : 8.0) / 1.0e6;
       const double scan_mb = static_cast<double>(tiles) * tile_mb;
       if (ctx->l2_keep_mb > 0.0 && scan_mb > ctx->l2_policy_min_mb && opt.max_iterations > 1)
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
@@ -672,6 +678,11 @@ int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem) {
   return CreateProblem(ctx, 0, 1, &capacity, false, problem);
 }
 
+int nlo_ndt_create_f32(nlo_context* ctx, int64_t capacity, nlo_problem** problem) {
+  if (capacity < 0) return Fail(ctx, NLO_EINVAL, "negative capacity");
+  return CreateProblem(ctx, 0, 1, &capacity, false, problem, true);
+}
+
 int nlo_ndt_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts, nlo_problem** problem) {
   if (counts == nullptr) return Fail(ctx, NLO_EINVAL, "null counts");
   return CreateProblem(ctx, 0, num_problems, counts, true, problem);
@@ -732,7 +743,7 @@ int nlo_ndt_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* p
     NLO_CUDA(ctx, cudaMemcpyAsync(s_sqrt, sqrt_info, 9 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (!pr->batched) {
-    NLO_CUDA(ctx, LaunchPackNdt(s_point, s_mean, s_sqrt, n, pr->planes, 0, ctx->stream));
+    NLO_CUDA(ctx, LaunchPackNdt(s_point, s_mean, s_sqrt, n, pr->planes, 0, pr->f32, ctx->stream));
     pr->n = n;
     pr->h_ranges[0] = Range{0, n};
   } else {
@@ -753,7 +764,8 @@ int nlo_ndt_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* p
 
 int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
                        size_t offset_point, size_t offset_mean, size_t offset_sqrt_info, int col_major) {
-  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched || pr->f32)
+    return Fail(ctx, NLO_EINVAL, "bad problem (AoS ingest needs a single fp64 NDT problem)");
   if (n < 0 || n > pr->counts[0] || (n > 0 && records == nullptr)) return Fail(ctx, NLO_EINVAL, "bad n / records");
   if (stride % 8 != 0 || offset_point % 8 != 0 || offset_mean % 8 != 0 || offset_sqrt_info % 8 != 0)
     return Fail(ctx, NLO_EINVAL, "record layout must be 8-byte aligned");
@@ -814,6 +826,7 @@ int GenerateCommon(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t glo
     const int64_t n = pr->batched ? pr->counts[b] : n_single;
     for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k];
     g.dst_offset = begin;
+    g.f32 = pr->f32 ? 1 : 0;
     g.n = n;
     g.seed = seed + static_cast<uint64_t>(b);
     g.index_offset = pr->batched ? 0 : global_index_offset;
@@ -859,7 +872,8 @@ int nlo_ndt_download(nlo_context* ctx, const nlo_problem* pr, int64_t begin, int
   double* s_point = static_cast<double*>(ctx->staging);
   double* s_mean = s_point + 3 * n;
   double* s_sqrt = s_mean + 3 * n;
-  NLO_CUDA(ctx, LaunchUnpackNdt(const_cast<double* const*>(pr->planes), begin, end, s_point, s_mean, s_sqrt, ctx->stream));
+  NLO_CUDA(ctx, LaunchUnpackNdt(const_cast<double* const*>(pr->planes), begin, end, s_point, s_mean, s_sqrt,
+                                pr->f32, ctx->stream));
   if (n > 0) {
     NLO_CUDA(ctx, cudaMemcpyAsync(point, s_point, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NLO_CUDA(ctx, cudaMemcpyAsync(mean, s_mean, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1173,7 +1187,7 @@ int nlo_ndt_match(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map
                   int32_t max_neighbors, nlo_problem* pr, int64_t* matched) {
   if (ctx == nullptr || scan == nullptr || map == nullptr || pose == nullptr || pr == nullptr)
     return Fail(ctx, NLO_EINVAL, "null argument");
-  if (pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "problem must be a single NDT problem");
+  if (pr->family != 0 || pr->batched || pr->f32) return Fail(ctx, NLO_EINVAL, "problem must be a single fp64 NDT problem");
   if (max_neighbors < 1 || max_neighbors > 2 || !(radius > 0.0)) return Fail(ctx, NLO_EINVAL, "bad radius / max_neighbors");
   if (static_cast<int64_t>(max_neighbors) * scan->n > pr->counts[0]) return Fail(ctx, NLO_EINVAL, "problem capacity too small");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -85,6 +85,7 @@ struct IterParams {
   int use_peer;
   unsigned long long* debug_times;  // nullable: [iterations][8] globaltimer stamps of CTA 0 (profiling aid)
   long long l2_keep_tiles;  // > 0: tiles [0, l2_keep_tiles) of the range are loaded evict_last, the rest evict_first
+  int f32;  // NDT planes stored as float (fp32 storage, fp64 math); planes[0] then points at float data
   int persistent;  // cooperative launch: the whole loop in one grid, grid barrier per iteration
   PeerComm peer;
 };
@@ -102,7 +103,7 @@ cudaError_t LaunchFinishStates(const State* states, double* poses16, double* res
                                int num_problems, int kind, cudaStream_t stream);
 cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
                           int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
-                          cudaStream_t stream);
+                          bool f32, cudaStream_t stream);
 cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
                                  int64_t n_total, const int64_t* src_prefix,
                                  const Range* ranges, int num_problems,
@@ -111,7 +112,8 @@ cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t str
                              size_t off_point, size_t off_mean, size_t off_sqrt, int col_major,
                              double* const planes[kNdtPlanes], cudaStream_t stream);
 cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int64_t end,
-                            double* point, double* mean, double* sqrt_info, cudaStream_t stream);
+                            double* point, double* mean, double* sqrt_info, bool f32,
+                            cudaStream_t stream);
 cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
                              double* const planes[kReprojPlanes], cudaStream_t stream);
 cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pixel, int64_t n_total,
@@ -121,6 +123,7 @@ cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pix
 struct GenerateParams {
   double* planes[kNdtPlanes];
   int64_t dst_offset;  // first correspondence index written (tile-aligned for batched problems)
+  int f32;             // planes hold floats
   int64_t n;
   uint64_t seed;
   int64_t index_offset;

@@ -116,22 +116,25 @@ struct KindTraits<kReproj> {
   static constexpr int kPlanes = kReprojPlanes, kAcc = kAcc6, kStages = 4, kTrace = 36;
 };
 
-template <int KIND>
+// ST = storage type of the planes in HBM and in the stages: double (parity mode, 120 B per NDT
+// correspondence) or float (fp32 storage, fp64 math: 60 B; twice the stages fit the same smem).
+template <int KIND, typename ST>
 struct SmemLayout {
   using T = KindTraits<KIND>;
-  double stages[T::kStages][T::kPlanes][kTile];
+  static constexpr int kStages = T::kStages * static_cast<int>(sizeof(double) / sizeof(ST));
+  ST stages[kStages][T::kPlanes][kTile];
   double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
   double total[32];            // reduced (raw, then canonical) sums
   State state;                 // CTA-local copy of the registration state
-  uint64_t full[T::kStages];
-  uint64_t empty[T::kStages];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
   unsigned int halves[kPeerWords];  // payload halves of the published state (LL words)
   int flag;
 };
 
-template <int KIND>
+template <int KIND, typename ST = double>
 constexpr size_t SmemBytes() {
-  return sizeof(SmemLayout<KIND>);
+  return sizeof(SmemLayout<KIND, ST>);
 }
 
 // One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
@@ -184,16 +187,16 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
   __syncthreads();
 }
 
-template <int KIND, int LOSS>
+template <int KIND, int LOSS, typename ST>
 __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = T::kPlanes;
-  constexpr int STAGES = T::kStages;
-  constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(double);
+  constexpr int STAGES = SmemLayout<KIND, ST>::kStages;
+  constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(ST);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout<KIND>& sm = *reinterpret_cast<SmemLayout<KIND>*>(smem_raw);
+  SmemLayout<KIND, ST>& sm = *reinterpret_cast<SmemLayout<KIND, ST>*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy.
           // l2_keep_tiles > 0: the scan is re-read every iteration and is larger than what the L2
           // keeps by itself -- pin the first tiles (evict_last), stream the rest (evict_first).
-          const double* src = p.planes[0] + tile * (NPLANES * kTile);
+          const ST* src = reinterpret_cast<const ST*>(p.planes[0]) + tile * (NPLANES * kTile);
           if (p.l2_keep_tiles > 0)
             BulkLoadHint(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s],
                          (tile - tile_lo) < p.l2_keep_tiles ? policy_keep : policy_stream);
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           }
           double v[NPLANES];
 #pragma unroll
-          for (int pl = 0; pl < NPLANES; ++pl) v[pl] = sm.stages[s][pl][tid];
+          for (int pl = 0; pl < NPLANES; ++pl) v[pl] = static_cast<double>(sm.stages[s][pl][tid]);
           if (!resident) {
             __syncwarp();
             if (lane == 0) MbarArrive(&sm.empty[s]);
@@ -526,18 +529,29 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int KIND, int LOSS>
-static cudaError_t LaunchOne(const IterParams& p, int grid_x, int num_problems,
-                             cudaStream_t stream) {
+template <int KIND, int LOSS, typename ST>
+static cudaError_t LaunchTyped(const IterParams& p, int grid_x, int num_problems,
+                               cudaStream_t stream) {
   dim3 grid(grid_x, num_problems);
   if (p.persistent) {
     IterParams copy = p;
     void* args[] = {&copy};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS>),
-                                       grid, dim3(kThreads), args, SmemBytes<KIND>(), stream);
+    return cudaLaunchCooperativeKernel(
+        reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, ST>), grid, dim3(kThreads),
+        args, SmemBytes<KIND, ST>(), stream);
   }
-  gn_iteration_kernel<KIND, LOSS><<<grid, kThreads, SmemBytes<KIND>(), stream>>>(p);
+  gn_iteration_kernel<KIND, LOSS, ST><<<grid, kThreads, SmemBytes<KIND, ST>(), stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int KIND, int LOSS>
+static cudaError_t LaunchOne(const IterParams& p, int grid_x, int num_problems,
+                             cudaStream_t stream) {
+  if (p.f32) {
+    if (KIND == kReproj) return cudaErrorInvalidValue;  // fp32 storage exists for the NDT kinds only
+    return LaunchTyped<(KIND == kReproj ? kNdt6 : KIND), LOSS, float>(p, grid_x, num_problems, stream);
+  }
+  return LaunchTyped<KIND, LOSS, double>(p, grid_x, num_problems, stream);
 }
 
 template <int KIND>
@@ -572,9 +586,13 @@ size_t IterationSmemBytes(int kind) {
 
 template <int KIND, int LOSS>
 static cudaError_t ConfigureOne() {
-  return cudaFuncSetAttribute(gn_iteration_kernel<KIND, LOSS>,
+  cudaError_t e = cudaFuncSetAttribute(gn_iteration_kernel<KIND, LOSS, double>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(SmemBytes<KIND, double>()));
+  if (e != cudaSuccess || KIND == kReproj) return e;
+  return cudaFuncSetAttribute(gn_iteration_kernel<(KIND == kReproj ? kNdt6 : KIND), LOSS, float>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(SmemBytes<KIND>()));
+                              static_cast<int>(SmemBytes<(KIND == kReproj ? kNdt6 : KIND), float>()));
 }
 template <int KIND>
 static cudaError_t ConfigureKind() {
@@ -664,18 +682,25 @@ struct PlanePtrs {
   double* p[kNdtPlanes];
 };
 
+// Element (plane k, correspondence i) of an NDT problem stored as ST.
+template <typename ST>
+__device__ __forceinline__ ST* NdtElem(double* plane0, int k, int64_t i) {
+  return reinterpret_cast<ST*>(plane0) + TiledOffset(kNdtPlanes, i) + k * kTile;
+}
+
+template <typename ST>
 __global__ void pack_ndt_kernel(const double* __restrict__ point, const double* __restrict__ mean,
                                 const double* __restrict__ sqrt_info, int64_t n, PlanePtrs planes,
                                 int64_t dst_offset) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t d = TiledOffset(kNdtPlanes, dst_offset + i);
+    const int64_t d = dst_offset + i;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * i + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<ST>(planes.p[0], k, d) = static_cast<ST>(point[3 * i + k]);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mean[3 * i + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<ST>(planes.p[0], 3 + k, d) = static_cast<ST>(mean[3 * i + k]);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) planes.p[6 + k][d] = sqrt_info[9 * i + k];
+    for (int k = 0; k < 9; ++k) *NdtElem<ST>(planes.p[0], 6 + k, d) = static_cast<ST>(sqrt_info[9 * i + k]);
   }
 }
 
@@ -722,16 +747,16 @@ __global__ void pack_ndt_aos_kernel(const unsigned char* __restrict__ records, i
   }
 }
 
+template <typename ST>
 __global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, double* point,
                                   double* mean, double* sqrt_info) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < end;
        i += stride) {
     const int64_t o = i - begin;
-    const int64_t d = TiledOffset(kNdtPlanes, i);
-    for (int k = 0; k < 3; ++k) point[3 * o + k] = planes.p[k][d];
-    for (int k = 0; k < 3; ++k) mean[3 * o + k] = planes.p[3 + k][d];
-    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = planes.p[6 + k][d];
+    for (int k = 0; k < 3; ++k) point[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], k, i));
+    for (int k = 0; k < 3; ++k) mean[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 3 + k, i));
+    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 6 + k, i));
   }
 }
 
@@ -782,10 +807,14 @@ static PlanePtrs MakePlanes(double* const* planes, int count) {
 
 cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
                           int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
-                          cudaStream_t stream) {
+                          bool f32, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  pack_ndt_kernel<<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
-                                                       MakePlanes(planes, kNdtPlanes), dst_offset);
+  if (f32)
+    pack_ndt_kernel<float><<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
+                                                                MakePlanes(planes, kNdtPlanes), dst_offset);
+  else
+    pack_ndt_kernel<double><<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
+                                                                 MakePlanes(planes, kNdtPlanes), dst_offset);
   return cudaGetLastError();
 }
 
@@ -814,10 +843,15 @@ cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t str
 }
 
 cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int64_t end,
-                            double* point, double* mean, double* sqrt_info, cudaStream_t stream) {
+                            double* point, double* mean, double* sqrt_info, bool f32,
+                            cudaStream_t stream) {
   if (end <= begin) return cudaSuccess;
-  unpack_ndt_kernel<<<GridFor(end - begin, 256), 256, 0, stream>>>(MakePlanes(planes, kNdtPlanes),
-                                                                  begin, end, point, mean, sqrt_info);
+  if (f32)
+    unpack_ndt_kernel<float><<<GridFor(end - begin, 256), 256, 0, stream>>>(
+        MakePlanes(planes, kNdtPlanes), begin, end, point, mean, sqrt_info);
+  else
+    unpack_ndt_kernel<double><<<GridFor(end - begin, 256), 256, 0, stream>>>(
+        MakePlanes(planes, kNdtPlanes), begin, end, point, mean, sqrt_info);
   return cudaGetLastError();
 }
 
@@ -926,10 +960,20 @@ __global__ void generate_ndt_kernel(const GenerateParams g) {
       }
     }
     // a point that never found a valid cell keeps S = 0 and contributes exactly nothing
-    const int64_t d = TiledOffset(kNdtPlanes, g.dst_offset + i);
-    g.planes[0][d] = lx; g.planes[1][d] = ly; g.planes[2][d] = lz;
-    for (int k = 0; k < 3; ++k) g.planes[3 + k][d] = mean[k];
-    for (int k = 0; k < 9; ++k) g.planes[6 + k][d] = S[k];
+    const int64_t d = g.dst_offset + i;
+    if (g.f32) {
+      *NdtElem<float>(g.planes[0], 0, d) = static_cast<float>(lx);
+      *NdtElem<float>(g.planes[0], 1, d) = static_cast<float>(ly);
+      *NdtElem<float>(g.planes[0], 2, d) = static_cast<float>(lz);
+      for (int k = 0; k < 3; ++k) *NdtElem<float>(g.planes[0], 3 + k, d) = static_cast<float>(mean[k]);
+      for (int k = 0; k < 9; ++k) *NdtElem<float>(g.planes[0], 6 + k, d) = static_cast<float>(S[k]);
+    } else {
+      *NdtElem<double>(g.planes[0], 0, d) = lx;
+      *NdtElem<double>(g.planes[0], 1, d) = ly;
+      *NdtElem<double>(g.planes[0], 2, d) = lz;
+      for (int k = 0; k < 3; ++k) *NdtElem<double>(g.planes[0], 3 + k, d) = mean[k];
+      for (int k = 0; k < 9; ++k) *NdtElem<double>(g.planes[0], 6 + k, d) = S[k];
+    }
   }
 }
 

@@ -513,3 +513,67 @@ def test_small_batch_uses_many_ctas_per_registration(ctx, nlo, oracle):
     assert out3["iterations"][0] == ref3[1]
     np.testing.assert_allclose(out3["poses"][0], ref3[0], rtol=0, atol=1e-6)
     prob.close()
+
+
+def _f32_round(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("n", [1, 255, 4097, 70001])
+def test_f32_storage_equals_oracle_on_float_rounded_inputs(ctx, nlo, oracle, n):
+    """Opt-in throughput mode: correspondences stored as float, arithmetic in fp64.  It must equal
+    the double oracle evaluated on the float-rounded inputs to the normal parity bar, and deviate
+    from the unrounded inputs only by the input quantisation."""
+    rng = np.random.default_rng(500 + n)
+    point, mean, S = syn.random_ndt_records(n, seed=900 + n)
+    pose16, R, t = _rand_pose(rng, nlo)
+    prob = nlo.NdtProblem(ctx, capacity=n, storage="f32")
+    prob.upload(point, mean, S)
+    p2, m2, s2 = prob.download(0, n)
+    np.testing.assert_array_equal(p2, _f32_round(point))
+    np.testing.assert_array_equal(s2, _f32_round(S))
+    Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
+    for loss in [(0, None), (1, [1.0, 1.0]), (2, [1.0])]:
+        ctx.set_loss(loss[0], loss[1])
+        H, g, c = prob.assemble6(pose16)
+        Hr, gr, cr = oracle.ndt6_assemble(_f32_round(point), _f32_round(mean), _f32_round(S), Rq, t,
+                                          loss[0], loss[1], long_double=True)
+        assert_sums_close(H, g, c, Hr, gr, cr)
+        H3, g3, c3 = prob.assemble3(syn.to_pose16(syn.yaw_pose([0.1, -0.1, 0.0], 0.05)))
+        T = syn.yaw_pose([0.1, -0.1, 0.0], 0.05)
+        Hr3, gr3, cr3 = oracle.ndt3_assemble(_f32_round(point), _f32_round(mean), _f32_round(S), T[:2, :2],
+                                             T[:2, 3], loss[0], loss[1], long_double=True)
+        assert_sums_close(H3, g3, c3, Hr3, gr3, cr3)
+    prob.close()
+
+
+def test_f32_storage_solve_trajectory_and_quantisation_error(ctx, nlo, oracle):
+    point, mean, S = syn.ndt_problem(100000, 1001, syn.CFG1_TRUE)
+    ctx.set_loss(1, [1.0, 1.0])
+    p32 = nlo.NdtProblem(ctx, capacity=len(point), storage="f32")
+    p32.upload(point, mean, S)
+    res = p32.solve6(nlo.identity_pose(), trace=True)
+    ref = oracle.ndt6_solve(_f32_round(point), _f32_round(mean), _f32_round(S), nlo.identity_pose(), 1, [1.0, 1.0])
+    _check_trajectory(res, ref, 36, nlo)
+    # against the unrounded double problem: only the input quantisation (float eps ~ 6e-8) shows
+    p64 = nlo.NdtProblem(ctx, capacity=len(point))
+    p64.upload(point, mean, S)
+    H32, g32, c32 = p32.assemble6(nlo.identity_pose())
+    H64, g64, c64 = p64.assemble6(nlo.identity_pose())
+    from parity import rel_errors
+    eh, eg, ec = rel_errors(H32, g32, c32, H64, g64, c64)
+    assert eh < 1e-6 and ec < 1e-6 and eg < 1e-4, (eh, eg, ec)
+    res64 = p64.solve6(nlo.identity_pose())
+    Ra, ta = nlo.pose_to_Rt(res["pose"]); Rb, tb = nlo.pose_to_Rt(res64["pose"])
+    assert np.max(np.abs(ta - tb)) < 1e-5 and rotation_angle(Ra, Rb) < 1e-5
+    # generated problems agree between the storage types up to the rounding of the stored values
+    grid = syn.room_ndt_grid(0.5)
+    g32p = nlo.NdtProblem(ctx, capacity=5000, storage="f32")
+    g64p = nlo.NdtProblem(ctx, capacity=5000)
+    for pr in (g32p, g64p):
+        pr.generate(5000, 9, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), nlo.identity_pose(), grid)
+    a = g32p.download(0, 5000); b = g64p.download(0, 5000)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, _f32_round(y))
+    for pr in (p32, p64, g32p, g64p):
+        pr.close()
