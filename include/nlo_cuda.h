@@ -108,6 +108,10 @@ NLO_API int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** pro
  * this is an opt-in throughput mode, not the parity mode.  Supported: upload, generate, download,
  * ndt6/ndt3 assemble and solve (single problem, also sharded over GPUs). */
 NLO_API int nlo_ndt_create_f32(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
+/* Upload into an fp32-storage problem from FLOAT host arrays (same record order as nlo_ndt_upload):
+ * half the PCIe bytes of the double upload. */
+NLO_API int nlo_ndt_upload_f32(nlo_context* ctx, nlo_problem* problem, int64_t n, const float* point,
+                       const float* mean, const float* sqrt_info);
 /* `num_problems` independent registrations; counts[k] correspondences each (BASELINE cfg5). */
 NLO_API int nlo_ndt_create_batched(nlo_context* ctx, int32_t num_problems, const int64_t* counts,
                            nlo_problem** problem);

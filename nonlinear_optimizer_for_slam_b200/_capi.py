@@ -46,6 +46,7 @@ _SIGNATURES = {
     "nlo_ndt_create_f32": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),
     "nlo_ndt_create_batched": (ctypes.c_int, [_VP, ctypes.c_int32, c_int64_p, ctypes.POINTER(_VP)]),
     "nlo_ndt_upload": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, _VP, _VP]),
+    "nlo_ndt_upload_f32": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, _VP, _VP]),
     "nlo_ndt_upload_aos": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, ctypes.c_size_t,
                                           ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
                                           ctypes.c_int]),

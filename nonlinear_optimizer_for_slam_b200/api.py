@@ -207,6 +207,19 @@ class NdtProblem(_Problem):
         self.ctx._check(self._lib.nlo_ndt_upload(self.ctx._h, self._h, n, point.ctypes.data,
                                                  mean.ctypes.data, sqrt_info.ctypes.data))
 
+    def upload_f32(self, point, mean, sqrt_info):
+        """Float host arrays into an fp32-storage problem (half the PCIe bytes)."""
+        point = np.ascontiguousarray(point, dtype=np.float32)
+        mean = np.ascontiguousarray(mean, dtype=np.float32)
+        sqrt_info = np.ascontiguousarray(sqrt_info, dtype=np.float32)
+        self.ctx._check(self._lib.nlo_ndt_upload_f32(self.ctx._h, self._h, point.size // 3,
+                                                     point.ctypes.data, mean.ctypes.data,
+                                                     sqrt_info.ctypes.data))
+
+    def upload_f32_ptr(self, n, point_ptr, mean_ptr, sqrt_info_ptr):
+        self.ctx._check(self._lib.nlo_ndt_upload_f32(self.ctx._h, self._h, n, point_ptr, mean_ptr,
+                                                     sqrt_info_ptr))
+
     def upload_ptr(self, n, point_ptr, mean_ptr, sqrt_info_ptr):
         """Upload from raw host pointers (e.g. pinned memory from nlo_host_alloc)."""
         self.ctx._check(self._lib.nlo_ndt_upload(self.ctx._h, self._h, n, point_ptr, mean_ptr,

@@ -762,6 +762,30 @@ int nlo_ndt_upload(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* p
   return NLO_OK;
 }
 
+int nlo_ndt_upload_f32(nlo_context* ctx, nlo_problem* pr, int64_t n, const float* point, const float* mean,
+                       const float* sqrt_info) {
+  if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched || !pr->f32)
+    return Fail(ctx, NLO_EINVAL, "bad problem (needs an fp32-storage NDT problem)");
+  if (n < 0 || n > pr->counts[0] || (n > 0 && (point == nullptr || mean == nullptr || sqrt_info == nullptr)))
+    return Fail(ctx, NLO_EINVAL, "bad n / null array");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 15 * sizeof(float) + 256);
+  if (rc != NLO_OK) return rc;
+  float* s_point = static_cast<float*>(ctx->staging);
+  float* s_mean = s_point + 3 * n;
+  float* s_sqrt = s_mean + 3 * n;
+  if (n > 0) {
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_point, point, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_mean, mean, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(s_sqrt, sqrt_info, 9 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NLO_CUDA(ctx, LaunchPackNdtFromFloat(s_point, s_mean, s_sqrt, n, pr->planes, ctx->stream));
+  }
+  pr->n = n;
+  pr->h_ranges[0] = Range{0, n};
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NLO_OK;
+}
+
 int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
                        size_t offset_point, size_t offset_mean, size_t offset_sqrt_info, int col_major) {
   if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched || pr->f32)

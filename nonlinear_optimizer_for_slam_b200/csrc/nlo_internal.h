@@ -104,6 +104,8 @@ cudaError_t LaunchFinishStates(const State* states, double* poses16, double* res
 cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
                           int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
                           bool f32, cudaStream_t stream);
+cudaError_t LaunchPackNdtFromFloat(const float* point, const float* mean, const float* sqrt_info,
+                                   int64_t n, double* const planes[kNdtPlanes], cudaStream_t stream);
 cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
                                  int64_t n_total, const int64_t* src_prefix,
                                  const Range* ranges, int num_problems,

@@ -704,6 +704,19 @@ __global__ void pack_ndt_kernel(const double* __restrict__ point, const double* 
   }
 }
 
+__global__ void pack_ndt_from_float_kernel(const float* __restrict__ point, const float* __restrict__ mean,
+                                           const float* __restrict__ sqrt_info, int64_t n, PlanePtrs planes) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], k, i) = point[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], 3 + k, i) = mean[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *NdtElem<float>(planes.p[0], 6 + k, i) = sqrt_info[9 * i + k];
+  }
+}
+
 // one CTA row per registration: source is the plain concatenation, destination is tile-aligned
 __global__ void pack_ndt_batched_kernel(const double* __restrict__ point,
                                         const double* __restrict__ mean,
@@ -815,6 +828,14 @@ cudaError_t LaunchPackNdt(const double* point, const double* mean, const double*
   else
     pack_ndt_kernel<double><<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
                                                                  MakePlanes(planes, kNdtPlanes), dst_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t LaunchPackNdtFromFloat(const float* point, const float* mean, const float* sqrt_info,
+                                   int64_t n, double* const planes[kNdtPlanes], cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pack_ndt_from_float_kernel<<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
+                                                                  MakePlanes(planes, kNdtPlanes));
   return cudaGetLastError();
 }
 

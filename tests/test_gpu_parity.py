@@ -532,6 +532,9 @@ def test_f32_storage_equals_oracle_on_float_rounded_inputs(ctx, nlo, oracle, n):
     p2, m2, s2 = prob.download(0, n)
     np.testing.assert_array_equal(p2, _f32_round(point))
     np.testing.assert_array_equal(s2, _f32_round(S))
+    prob.upload_f32(point, mean, S)           # float host arrays give the same device contents
+    p3, m3, s3 = prob.download(0, n)
+    assert np.array_equal(p3, p2) and np.array_equal(m3, m2) and np.array_equal(s3, s2)
     Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
     for loss in [(0, None), (1, [1.0, 1.0]), (2, [1.0])]:
         ctx.set_loss(loss[0], loss[1])
