@@ -19,7 +19,8 @@
  *   - host arrays use the reference's record order: point[3n] xyz interleaved, mean[3n],
  *     sqrt_info[9n] ROW-major 3x3 per correspondence (S(i,j) at 9k+3i+j), local_point[3n],
  *     pixel[2n].  On the device they are repacked into a tile-interleaved SoA layout (DESIGN.md
- *     section 2): 256 correspondences per tile, the 15 (5) planes of a tile back to back.
+ *     section 2): 256 correspondences per tile, the planes of a tile back to back; an NDT record
+ *     becomes 12 doubles (point 3, mean 3, the 6 unique entries of S^T S formed once at ingest).
  *   - H is the packed upper triangle in row-major order: 6-DoF 21 values
  *     (0,0),(0,1)..(0,5),(1,1)..(5,5); 3-DoF 6 values.  g is J^T W r (6 or 3).
  *   - a context owns one CUDA device + one stream; calls on one context are serialised by the
@@ -144,9 +145,11 @@ NLO_API int nlo_ndt_generate_batched(nlo_context* ctx, nlo_problem* problem, uin
                              const int32_t grid_dims[3], double voxel_size,
                              const double* cell_mean, const double* cell_sqrt_info,
                              const uint8_t* cell_valid);
-/* Device -> host copy of correspondences [begin, end) in the host array convention (tests). */
+/* Device -> host copy of correspondences [begin, end) (tests): point[3n], mean[3n] and the 6
+ * unique entries of the information matrix S^T S per correspondence (00 01 02 11 12 22) -- the
+ * device keeps S only through S^T S, which is all both NDT minimizers use. */
 NLO_API int nlo_ndt_download(nlo_context* ctx, const nlo_problem* problem, int64_t begin, int64_t end,
-                     double* point, double* mean, double* sqrt_info);
+                     double* point, double* mean, double* information);
 
 /* ---- reprojection correspondences (reprojection_error_minimizer/types.h:14-28) ---- */
 NLO_API int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);

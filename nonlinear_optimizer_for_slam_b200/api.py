@@ -254,11 +254,12 @@ class NdtProblem(_Problem):
             valid.ctypes.data_as(_capi.c_uint8_p)))
 
     def download(self, begin, end):
+        """point[n,3], mean[n,3], information[n,6] = unique entries (00 01 02 11 12 22) of S^T S."""
         n = end - begin
-        point = np.zeros((n, 3)); mean = np.zeros((n, 3)); sq = np.zeros((n, 9))
+        point = np.zeros((n, 3)); mean = np.zeros((n, 3)); info = np.zeros((n, 6))
         self.ctx._check(self._lib.nlo_ndt_download(self.ctx._h, self._h, begin, end, _dp(point),
-                                                   _dp(mean), _dp(sq)))
-        return point, mean, sq
+                                                   _dp(mean), _dp(info)))
+        return point, mean, info
 
     def assemble6(self, pose16, begin=0, end=None, problem_index=0):
         """..._analytic.cc:12-52 over [begin, end)."""

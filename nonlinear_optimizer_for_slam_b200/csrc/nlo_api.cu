@@ -196,7 +196,7 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   nlo_problem* pr = new nlo_problem();
   pr->family = family;
-  pr->num_planes = (family == 0) ? kNdtPlanes : kReprojPlanes;
+  pr->num_planes = (family == 0) ? (f32 ? kNdtPlanes : kNdtPlanesF64) : kReprojPlanes;
   pr->num_problems = num_problems;
   pr->batched = batched;
   pr->f32 = f32;
@@ -848,7 +848,7 @@ int GenerateCommon(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t glo
   for (int b = 0; b < B; ++b) {
     const int64_t begin = pr->batched ? pr->h_ranges[b].begin : 0;
     const int64_t n = pr->batched ? pr->counts[b] : n_single;
-    for (int k = 0; k < kNdtPlanes; ++k) g.planes[k] = pr->planes[k];
+    for (int k = 0; k < pr->num_planes; ++k) g.planes[k] = pr->planes[k];
     g.dst_offset = begin;
     g.f32 = pr->f32 ? 1 : 0;
     g.n = n;
@@ -885,23 +885,23 @@ int nlo_ndt_generate_batched(nlo_context* ctx, nlo_problem* pr, uint64_t seed, d
 }
 
 int nlo_ndt_download(nlo_context* ctx, const nlo_problem* pr, int64_t begin, int64_t end, double* point,
-                     double* mean, double* sqrt_info) {
+                     double* mean, double* information) {
   if (ctx == nullptr || pr == nullptr || pr->family != 0 || pr->batched) return Fail(ctx, NLO_EINVAL, "bad problem");
   if (begin < 0 || end < begin || end > pr->n) return Fail(ctx, NLO_EINVAL, "bad [begin, end)");
-  if (!point || !mean || !sqrt_info) return Fail(ctx, NLO_EINVAL, "null array");
+  if (!point || !mean || !information) return Fail(ctx, NLO_EINVAL, "null array");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t n = end - begin;
-  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 15 * sizeof(double) + 256);
+  int rc = EnsureStaging(ctx, static_cast<size_t>(n) * 12 * sizeof(double) + 256);
   if (rc != NLO_OK) return rc;
   double* s_point = static_cast<double*>(ctx->staging);
   double* s_mean = s_point + 3 * n;
-  double* s_sqrt = s_mean + 3 * n;
-  NLO_CUDA(ctx, LaunchUnpackNdt(const_cast<double* const*>(pr->planes), begin, end, s_point, s_mean, s_sqrt,
+  double* s_info = s_mean + 3 * n;
+  NLO_CUDA(ctx, LaunchUnpackNdt(const_cast<double* const*>(pr->planes), begin, end, s_point, s_mean, s_info,
                                 pr->f32, ctx->stream));
   if (n > 0) {
     NLO_CUDA(ctx, cudaMemcpyAsync(point, s_point, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NLO_CUDA(ctx, cudaMemcpyAsync(mean, s_mean, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    NLO_CUDA(ctx, cudaMemcpyAsync(sqrt_info, s_sqrt, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NLO_CUDA(ctx, cudaMemcpyAsync(information, s_info, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NLO_OK;
@@ -1012,7 +1012,7 @@ int MatchInto(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map, co
   memset(&mp, 0, sizeof(mp));
   for (int k = 0; k < 3; ++k) mp.scan[k] = scan->planes[k];
   mp.n = scan->n;
-  for (int k = 0; k < kNdtPlanes; ++k) mp.planes[k] = pr->planes[k];
+  for (int k = 0; k < pr->num_planes; ++k) mp.planes[k] = pr->planes[k];
   PoseToRt(pose, mp.R, mp.t);
   for (int k = 0; k < 3; ++k) { mp.origin[k] = map->origin[k]; mp.dims[k] = map->dims[k]; }
   mp.inv_voxel = 1.0 / map->voxel;

@@ -105,24 +105,32 @@ template <int KIND>
 struct KindTraits;
 template <>
 struct KindTraits<kNdt6> {
-  static constexpr int kPlanes = kNdtPlanes, kAcc = kAcc6, kStages = 3, kTrace = 36;
+  static constexpr int kAcc = kAcc6, kStages = 3, kTrace = 36;
 };
 template <>
 struct KindTraits<kNdt3> {
-  static constexpr int kPlanes = kNdtPlanes, kAcc = kAcc3, kStages = 3, kTrace = 17;
+  static constexpr int kAcc = kAcc3, kStages = 3, kTrace = 17;
 };
 template <>
 struct KindTraits<kReproj> {
-  static constexpr int kPlanes = kReprojPlanes, kAcc = kAcc6, kStages = 4, kTrace = 36;
+  static constexpr int kAcc = kAcc6, kStages = 4, kTrace = 36;
 };
+
+// Planes of one correspondence for a kind and a storage type.
+template <int KIND, typename ST>
+__host__ __device__ constexpr int PlanesOf() {
+  return KIND == kReproj ? kReprojPlanes : (sizeof(ST) == 8 ? kNdtPlanesF64 : kNdtPlanes);
+}
 
 // ST = storage type of the planes in HBM and in the stages: double (parity mode, 120 B per NDT
 // correspondence) or float (fp32 storage, fp64 math: 60 B; twice the stages fit the same smem).
 template <int KIND, typename ST>
 struct SmemLayout {
   using T = KindTraits<KIND>;
-  static constexpr int kStages = T::kStages * static_cast<int>(sizeof(double) / sizeof(ST));
-  ST stages[kStages][T::kPlanes][kTile];
+  // bytes per stage: NDT fp64 24 KB (12 planes), NDT fp32 15 KB (15 planes), PnP 10 KB; two CTAs
+  // per SM share the 227 KB
+  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? 4 : 6);
+  ST stages[kStages][PlanesOf<KIND, ST>()][kTile];
   double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
   double total[32];            // reduced (raw, then canonical) sums
   State state;                 // CTA-local copy of the registration state
@@ -191,7 +199,8 @@ template <int KIND, int LOSS, typename ST>
 __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
-  constexpr int NPLANES = T::kPlanes;
+  constexpr int NPLANES = PlanesOf<KIND, ST>();
+  constexpr bool HAS_L = sizeof(ST) == 8;  // fp64 storage carries S^T S, fp32 storage carries S
   constexpr int STAGES = SmemLayout<KIND, ST>::kStages;
   constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(ST);
 
@@ -310,9 +319,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
               (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
           const bool valid = (idx >= range.begin) && (idx < range.end);
           if (KIND == kNdt6)
-            Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            Ndt6Point<LOSS, HAS_L>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
           else if (KIND == kNdt3)
-            Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            Ndt3Point<LOSS, HAS_L>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
           else
             ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
         }
@@ -685,7 +694,23 @@ struct PlanePtrs {
 // Element (plane k, correspondence i) of an NDT problem stored as ST.
 template <typename ST>
 __device__ __forceinline__ ST* NdtElem(double* plane0, int k, int64_t i) {
-  return reinterpret_cast<ST*>(plane0) + TiledOffset(kNdtPlanes, i) + k * kTile;
+  return reinterpret_cast<ST*>(plane0) + TiledOffset(PlanesOf<kNdt6, ST>(), i) + k * kTile;
+}
+
+// Stores the information part of an NDT record from its sqrt_information S (row-major):
+// fp64 storage keeps the 6 unique entries of L = S^T S, fp32 storage keeps the 9 entries of S.
+template <typename ST>
+__device__ __forceinline__ void StoreNdtInformation(double* plane0, int64_t i, const double* S) {
+  if (sizeof(ST) == 8) {
+    const double L[6] = {S[0] * S[0] + S[3] * S[3] + S[6] * S[6], S[0] * S[1] + S[3] * S[4] + S[6] * S[7],
+                         S[0] * S[2] + S[3] * S[5] + S[6] * S[8], S[1] * S[1] + S[4] * S[4] + S[7] * S[7],
+                         S[1] * S[2] + S[4] * S[5] + S[7] * S[8], S[2] * S[2] + S[5] * S[5] + S[8] * S[8]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) *NdtElem<ST>(plane0, 6 + k, i) = static_cast<ST>(L[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *NdtElem<ST>(plane0, 6 + k, i) = static_cast<ST>(S[k]);
+  }
 }
 
 template <typename ST>
@@ -699,8 +724,10 @@ __global__ void pack_ndt_kernel(const double* __restrict__ point, const double* 
     for (int k = 0; k < 3; ++k) *NdtElem<ST>(planes.p[0], k, d) = static_cast<ST>(point[3 * i + k]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) *NdtElem<ST>(planes.p[0], 3 + k, d) = static_cast<ST>(mean[3 * i + k]);
+    double S[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) *NdtElem<ST>(planes.p[0], 6 + k, d) = static_cast<ST>(sqrt_info[9 * i + k]);
+    for (int k = 0; k < 9; ++k) S[k] = sqrt_info[9 * i + k];
+    StoreNdtInformation<ST>(planes.p[0], d, S);
   }
 }
 
@@ -729,13 +756,15 @@ __global__ void pack_ndt_batched_kernel(const double* __restrict__ point,
   const int64_t dst0 = ranges[b].begin;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t s = src0 + i, d = TiledOffset(kNdtPlanes, dst0 + i);
+    const int64_t s = src0 + i, d = dst0 + i;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[k][d] = point[3 * s + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], k, d) = point[3 * s + k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mean[3 * s + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], 3 + k, d) = mean[3 * s + k];
+    double S[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) planes.p[6 + k][d] = sqrt_info[9 * s + k];
+    for (int k = 0; k < 9; ++k) S[k] = sqrt_info[9 * s + k];
+    StoreNdtInformation<double>(planes.p[0], d, S);
   }
 }
 
@@ -745,18 +774,19 @@ __global__ void pack_ndt_aos_kernel(const unsigned char* __restrict__ records, i
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const unsigned char* rec = records + static_cast<size_t>(i) * stride_bytes;
-    const int64_t d = TiledOffset(kNdtPlanes, i);
     const double* pt = reinterpret_cast<const double*>(rec + off_point);
     const double* mu = reinterpret_cast<const double*>(rec + off_mean);
     const double* S = reinterpret_cast<const double*>(rec + off_sqrt);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[k][d] = pt[k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], k, i) = pt[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) planes.p[3 + k][d] = mu[k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], 3 + k, i) = mu[k];
+    double Srow[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) planes.p[6 + 3 * r + c][d] = col_major ? S[3 * c + r] : S[3 * r + c];
+      for (int c = 0; c < 3; ++c) Srow[3 * r + c] = col_major ? S[3 * c + r] : S[3 * r + c];
+    StoreNdtInformation<double>(planes.p[0], i, Srow);
   }
 }
 
@@ -769,7 +799,15 @@ __global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, 
     const int64_t o = i - begin;
     for (int k = 0; k < 3; ++k) point[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], k, i));
     for (int k = 0; k < 3; ++k) mean[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 3 + k, i));
-    for (int k = 0; k < 9; ++k) sqrt_info[9 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 6 + k, i));
+    // third output: the 6 unique entries of the information matrix S^T S (00 01 02 11 12 22)
+    if (sizeof(ST) == 8) {
+      for (int k = 0; k < 6; ++k) sqrt_info[6 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 6 + k, i));
+    } else {
+      double v[15];
+      for (int k = 6; k < 15; ++k) v[k] = static_cast<double>(*NdtElem<ST>(planes.p[0], k, i));
+      NdtInformation<false>(v, sqrt_info[6 * o], sqrt_info[6 * o + 1], sqrt_info[6 * o + 2], sqrt_info[6 * o + 3],
+                            sqrt_info[6 * o + 4], sqrt_info[6 * o + 5]);
+    }
   }
 }
 
@@ -987,13 +1025,13 @@ __global__ void generate_ndt_kernel(const GenerateParams g) {
       *NdtElem<float>(g.planes[0], 1, d) = static_cast<float>(ly);
       *NdtElem<float>(g.planes[0], 2, d) = static_cast<float>(lz);
       for (int k = 0; k < 3; ++k) *NdtElem<float>(g.planes[0], 3 + k, d) = static_cast<float>(mean[k]);
-      for (int k = 0; k < 9; ++k) *NdtElem<float>(g.planes[0], 6 + k, d) = static_cast<float>(S[k]);
+      StoreNdtInformation<float>(g.planes[0], d, S);
     } else {
       *NdtElem<double>(g.planes[0], 0, d) = lx;
       *NdtElem<double>(g.planes[0], 1, d) = ly;
       *NdtElem<double>(g.planes[0], 2, d) = lz;
       for (int k = 0; k < 3; ++k) *NdtElem<double>(g.planes[0], 3 + k, d) = mean[k];
-      for (int k = 0; k < 9; ++k) *NdtElem<double>(g.planes[0], 6 + k, d) = S[k];
+      StoreNdtInformation<double>(g.planes[0], d, S);
     }
   }
 }
@@ -1049,16 +1087,20 @@ __global__ void match_ndt_kernel(const MatchParams m) {
       }
     }
     for (int j = 0; j < m.max_neighbors; ++j) {
-      const int64_t o = TiledOffset(kNdtPlanes, static_cast<int64_t>(j) * m.n + i);
+      const int64_t o = static_cast<int64_t>(j) * m.n + i;
       const int c = best[j];
-      m.planes[0][o] = lx; m.planes[1][o] = ly; m.planes[2][o] = lz;
+      *NdtElem<double>(m.planes[0], 0, o) = lx;
+      *NdtElem<double>(m.planes[0], 1, o) = ly;
+      *NdtElem<double>(m.planes[0], 2, o) = lz;
+      double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      double mu[3] = {0, 0, 0};
       if (c >= 0) {
-        for (int k = 0; k < 3; ++k) m.planes[3 + k][o] = m.cell_mean[3 * c + k];
-        for (int k = 0; k < 9; ++k) m.planes[6 + k][o] = m.cell_sqrt_info[9 * c + k];
+        for (int k = 0; k < 3; ++k) mu[k] = m.cell_mean[3 * c + k];
+        for (int k = 0; k < 9; ++k) S[k] = m.cell_sqrt_info[9 * c + k];
         ++local_matched;
-      } else {
-        for (int k = 3; k < kNdtPlanes; ++k) m.planes[k][o] = 0.0;
       }
+      for (int k = 0; k < 3; ++k) *NdtElem<double>(m.planes[0], 3 + k, o) = mu[k];
+      StoreNdtInformation<double>(m.planes[0], o, S);
     }
   }
   if (m.matched != nullptr) {

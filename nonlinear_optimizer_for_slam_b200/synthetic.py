@@ -241,3 +241,25 @@ def random_rotation(rng, max_angle=0.5):
     ang = rng.uniform(-max_angle, max_angle)
     K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
     return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+
+def information6(sqrt_info):
+    """Unique entries (00 01 02 11 12 22) of S^T S for row-major S[n,9] -- what the device stores."""
+    S = np.asarray(sqrt_info, dtype=np.float64).reshape(-1, 3, 3)
+    L = np.einsum("nki,nkj->nij", S, S)
+    return np.stack([L[:, 0, 0], L[:, 0, 1], L[:, 0, 2], L[:, 1, 1], L[:, 1, 2], L[:, 2, 2]], 1)
+
+
+def sqrt_info_from_information6(info6):
+    """A sqrt_information (row-major [n,9]) with S^T S equal to the given information matrices:
+    the upper Cholesky factor (rank-deficient / zero records map to zero rows)."""
+    L6 = np.asarray(info6, dtype=np.float64).reshape(-1, 6)
+    n = len(L6)
+    L = np.zeros((n, 3, 3))
+    L[:, 0, 0] = L6[:, 0]; L[:, 0, 1] = L[:, 1, 0] = L6[:, 1]; L[:, 0, 2] = L[:, 2, 0] = L6[:, 2]
+    L[:, 1, 1] = L6[:, 3]; L[:, 1, 2] = L[:, 2, 1] = L6[:, 4]; L[:, 2, 2] = L6[:, 5]
+    S = np.zeros((n, 3, 3))
+    ok = np.linalg.det(L) > 1e-300
+    if ok.any():
+        S[ok] = np.transpose(np.linalg.cholesky(L[ok]), (0, 2, 1))
+    return S.reshape(n, 9)

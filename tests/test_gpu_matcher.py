@@ -40,14 +40,17 @@ def test_match_equals_exhaustive_search(ctx, nlo, voxel):
     matched = scan.match(ndt_map, syn.to_pose16(T), prob)
     ref = brute_force_match(local, T, grid)
     assert matched == int((ref >= 0).sum())
-    point, mean, S = prob.download(0, 2 * len(local))
+    point, mean, info = prob.download(0, 2 * len(local))
     n = len(local)
+    cell_info = syn.information6(grid["sqrt_info"])
     for j in range(2):
         has = ref[:, j] >= 0
         np.testing.assert_array_equal(point[j * n:(j + 1) * n], local)
         np.testing.assert_array_equal(mean[j * n:(j + 1) * n][has], grid["mean"][ref[has, j]])
-        np.testing.assert_array_equal(S[j * n:(j + 1) * n][has], grid["sqrt_info"][ref[has, j]])
-        assert not S[j * n:(j + 1) * n][~has].any()
+        # entries that cancel to ~0 differ in the last bits between numpy and the device (FMA)
+        np.testing.assert_allclose(info[j * n:(j + 1) * n][has], cell_info[ref[has, j]], rtol=1e-13,
+                                   atol=1e-13 * np.abs(cell_info).max())
+        assert not info[j * n:(j + 1) * n][~has].any()
     prob.close(); scan.close(); ndt_map.close()
 
 

@@ -210,10 +210,15 @@ def test_upload_aos_reference_layout(ctx, nlo, oracle):
     rec[:, off_sqrt:off_sqrt + 72] = S_col.view(np.uint8).reshape(n, 72)
     prob = nlo.NdtProblem(ctx, capacity=n)
     prob.upload_aos(rec, n, stride, off_point, off_mean, off_sqrt, True)
-    p2, m2, s2 = prob.download(0, n)
+    p2, m2, info = prob.download(0, n)
     np.testing.assert_array_equal(p2, point)
     np.testing.assert_array_equal(m2, mean)
-    np.testing.assert_array_equal(s2, S)
+    # the device keeps S only through the information matrix S^T S (formed once at ingest)
+    np.testing.assert_allclose(info, syn.information6(S), rtol=1e-13, atol=1e-13 * np.abs(S).max() ** 2)
+    ctx.set_loss(1, [1.0, 1.0])
+    H, g, c = prob.assemble6(nlo.identity_pose())
+    Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, np.eye(3), np.zeros(3), 1, [1.0, 1.0], long_double=True)
+    assert_sums_close(H, g, c, Hr, gr, cr)
     prob.close()
 
 
@@ -223,16 +228,17 @@ def test_generate_matches_host_association(ctx, nlo):
     prob = nlo.NdtProblem(ctx, capacity=n)
     true16 = syn.to_pose16(syn.CFG1_TRUE)
     prob.generate(n, 1004, 0, 0.01, true16, nlo.identity_pose(), grid)
-    point, mean, S = prob.download(0, n)
+    point, mean, info = prob.download(0, n)
     # points lie on the room surfaces (in the world frame) up to the noise
     w = point @ syn.CFG1_TRUE[:3, :3].T + syn.CFG1_TRUE[:3, 3]
     d = np.minimum.reduce([np.abs(w[:, 2]), np.abs(w[:, 1] + 2.5), np.abs(w[:, 1] - 2.5),
                            np.abs(w[:, 0] + 3.5), np.abs(w[:, 0] - 3.5)])
     assert d.max() < 0.08 and 0.004 < d.std() < 0.02
     _, m_ref, s_ref = syn.associate_dense(point, np.eye(4), grid, keep_unmatched=True)
-    mismatch = np.any(mean != m_ref, axis=1) | np.any(S != s_ref, axis=1)
+    info_ref = syn.information6(s_ref)
+    mismatch = np.any(mean != m_ref, axis=1) | np.any(np.abs(info - info_ref) > 1e-12 * (1 + np.abs(info_ref)), axis=1)
     assert mismatch.mean() < 1e-4
-    assert (np.abs(S).sum(1) > 0).mean() > 0.99
+    assert (np.abs(info).sum(1) > 0).mean() > 0.99
     # a different offset continues the same stream
     prob2 = nlo.NdtProblem(ctx, capacity=1000)
     prob2.generate(1000, 1004, 5000, 0.01, true16, nlo.identity_pose(), grid)
@@ -279,7 +285,9 @@ def test_batched_copies_are_identical_and_match_single(ctx, nlo):
     # every registration from the same stream: seeds differ by +k, so rebuild with equal seeds
     single = nlo.NdtProblem(ctx, capacity=n)
     single.generate(n, 77, 0, 0.01, true[0], nlo.identity_pose(), grid)
-    p, m, s = single.download(0, n)
+    p, m, info = single.download(0, n)
+    s = syn.sqrt_info_from_information6(info)
+    single.upload(p, m, s)                      # both sides from the same host arrays
     prob.upload(np.tile(p, (B, 1)), np.tile(m, (B, 1)), np.tile(s, (B, 1)))
     out = prob.solve6_batched(np.tile(nlo.identity_pose(), (B, 1)))
     assert np.all(out["iterations"] == out["iterations"][0])
@@ -305,7 +313,8 @@ def test_batched_generate_matches_single_generate(ctx, nlo, oracle):
     for k, c in enumerate(counts):
         single = nlo.NdtProblem(ctx, capacity=c)
         single.generate(c, 2000 + k, 0, 0.01, true[k], nlo.identity_pose(), grid)
-        p, m, s = single.download(0, c)
+        p, m, info = single.download(0, c)
+        s = syn.sqrt_info_from_information6(info)   # any S with S^T S = information is equivalent
         pose_r, it_r, cost_r, _ = oracle.ndt6_solve(p, m, s, nlo.identity_pose(), 1, [1.0, 1.0])
         assert out["iterations"][k] == it_r
         Ra, ta = nlo.pose_to_Rt(out["poses"][k]); Rb, tb = nlo.pose_to_Rt(pose_r)
@@ -529,12 +538,12 @@ def test_f32_storage_equals_oracle_on_float_rounded_inputs(ctx, nlo, oracle, n):
     pose16, R, t = _rand_pose(rng, nlo)
     prob = nlo.NdtProblem(ctx, capacity=n, storage="f32")
     prob.upload(point, mean, S)
-    p2, m2, s2 = prob.download(0, n)
+    p2, m2, i2 = prob.download(0, n)
     np.testing.assert_array_equal(p2, _f32_round(point))
-    np.testing.assert_array_equal(s2, _f32_round(S))
+    np.testing.assert_allclose(i2, syn.information6(_f32_round(S)), rtol=1e-13, atol=1e-13 * np.abs(S).max() ** 2)
     prob.upload_f32(point, mean, S)           # float host arrays give the same device contents
-    p3, m3, s3 = prob.download(0, n)
-    assert np.array_equal(p3, p2) and np.array_equal(m3, m2) and np.array_equal(s3, s2)
+    p3, m3, i3 = prob.download(0, n)
+    assert np.array_equal(p3, p2) and np.array_equal(m3, m2) and np.array_equal(i3, i2)
     Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
     for loss in [(0, None), (1, [1.0, 1.0]), (2, [1.0])]:
         ctx.set_loss(loss[0], loss[1])
@@ -576,7 +585,9 @@ def test_f32_storage_solve_trajectory_and_quantisation_error(ctx, nlo, oracle):
     for pr in (g32p, g64p):
         pr.generate(5000, 9, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), nlo.identity_pose(), grid)
     a = g32p.download(0, 5000); b = g64p.download(0, 5000)
-    for x, y in zip(a, b):
-        np.testing.assert_array_equal(x, _f32_round(y))
+    np.testing.assert_array_equal(a[0], _f32_round(b[0]))
+    np.testing.assert_array_equal(a[1], _f32_round(b[1]))
+    # information of float-rounded S vs of S (entries that cancel to ~0 need an absolute scale)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-6, atol=1e-6 * np.abs(b[2]).max())
     for pr in (p32, p64, g32p, g64p):
         pr.close()
