@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnlo_cuda.so")
+LIB_PATH = os.environ.get("NLO_LIB", os.path.join(_PKG, "libnlo_cuda.so"))
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)

@@ -87,6 +87,7 @@ struct IterParams {
   int use_peer;
   unsigned long long* debug_times;  // nullable: [iterations][8] globaltimer stamps of CTA 0 (profiling aid)
   long long l2_keep_tiles;  // > 0: tiles [0, l2_keep_tiles) of the range are loaded evict_last, the rest evict_first
+  int stage_depth;  // > 0: use only this many of the allocated shared-memory stages
   int f32;  // NDT planes stored as float (fp32 storage, fp64 math); planes[0] then points at float data
   int persistent;  // cooperative launch: the whole loop in one grid, grid barrier per iteration
   PeerComm peer;

@@ -129,7 +129,10 @@ struct SmemLayout {
   using T = KindTraits<KIND>;
   // bytes per stage: NDT fp64 24 KB (12 planes), NDT fp32 15 KB (15 planes), PnP 10 KB; two CTAs
   // per SM share the 227 KB
-  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? 4 : 6);
+#ifndef NLO_NDT_STAGES
+#define NLO_NDT_STAGES 4
+#endif
+  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? NLO_NDT_STAGES : 6);
   ST stages[kStages][PlanesOf<KIND, ST>()][kTile];
   double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
   double total[32];            // reduced (raw, then canonical) sums
@@ -201,7 +204,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = PlanesOf<KIND, ST>();
   constexpr bool HAS_L = sizeof(ST) == 8;  // fp64 storage carries S^T S, fp32 storage carries S
-  constexpr int STAGES = SmemLayout<KIND, ST>::kStages;
+  constexpr int MAX_STAGES = SmemLayout<KIND, ST>::kStages;
+  // ring depth actually used (<= the stages allocated): chosen per launch shape by the host
+  const int STAGES = (p.stage_depth > 0 && p.stage_depth < MAX_STAGES) ? p.stage_depth : MAX_STAGES;
   constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(ST);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
 
   if (tid == 0) {
     if (p.mode != kModeStepOnly) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < MAX_STAGES; ++s) {
         MbarInit(&sm.full[s], 1);
         MbarInit(&sm.empty[s], kConsumerWarps);
       }
@@ -244,7 +249,10 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   } while (0)
 
   const uint64_t policy_keep = PolicyEvictLast(), policy_stream = PolicyEvictFirst();
-  uint32_t ring = 0;  // tiles consumed so far by this CTA (keeps mbarrier phases across iterations)
+  // Ring positions are carried incrementally (no divisions in the tile loop): the consumers'
+  // next (stage, phase) and -- thread 0 only -- the producer's, which runs STAGES-1 tiles ahead.
+  int c_stage = 0, p_stage = 0;
+  uint32_t c_phase = 0, p_phase = 0;
   // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
   // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
   const bool resident = (p.iterations_in_kernel > 1) && (my_tiles <= STAGES);
@@ -265,9 +273,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       {
         // Producer duty (thread 0): keep STAGES-1 tiles in flight ahead of the tile being consumed.
         auto issue_tile = [&](int m) {
-          const uint32_t k = ring + m;
-          const int s = k % STAGES;
-          const uint32_t phase = (k / STAGES) & 1u;
+          const int s = p_stage;
+          const uint32_t phase = p_phase;
+          if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1u; }
           MbarWait(&sm.empty[s], phase ^ 1u);
           MbarExpectTx(&sm.full[s], kStageBytes);
           const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
@@ -300,9 +308,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           for (int k = 0; k < 3; ++k) t[k] = st.t[k];
         }
         for (int m = 0; m < my_tiles; ++m) {
-          const uint32_t k = ring + m;
-          const int s = k % STAGES;
-          const uint32_t phase = (k / STAGES) & 1u;
+          const int s = resident ? m : c_stage;
+          const uint32_t phase = c_phase;
+          if (!resident && ++c_stage == STAGES) { c_stage = 0; c_phase ^= 1u; }
           if (need_load) {
             if (tid == 0 && m + STAGES - 1 < my_tiles) issue_tile(m + STAGES - 1);
             __syncwarp();
@@ -350,7 +358,6 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           if (lane < NACC) sm.warp_sums[warp][lane] = v[0];
         }
         if (!resident) {
-          ring += my_tiles;
           if (it + 1 < p.iterations_in_kernel && p.mode == kModeSolve) {
             const int ahead = (my_tiles < STAGES - 1) ? my_tiles : STAGES - 1;
             if (tid == 0)
@@ -531,8 +538,8 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   // a prefetch may still be in flight when the loop ends early: let it land before the CTA exits
   if (prefetched > 0) {
     for (int m = 0; m < prefetched; ++m) {
-      const uint32_t k = ring + m;
-      MbarWait(&sm.full[k % STAGES], (k / STAGES) & 1u);
+      MbarWait(&sm.full[c_stage], c_phase);
+      if (++c_stage == STAGES) { c_stage = 0; c_phase ^= 1u; }
     }
   }
 }

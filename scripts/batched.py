@@ -40,7 +40,7 @@ def main():
         print("%s: B=%d n=%d  device %.3f ms (wall %.3f ms)  iterations min/mean/max %d/%.1f/%d  "
               "%.2f Gpoints/s  %.0f GB/s  %.0f registrations/s"
               % (label, B, n, ms, wall * 1e3, iters.min(), iters.mean(), iters.max(),
-                 work / ms / 1e6, work * 120 / ms / 1e6, B / ms * 1e3))
+                 work / ms / 1e6, work * 96 / ms / 1e6, B / ms * 1e3))
     prob.close(); ctx.close()
 
 

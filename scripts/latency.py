@@ -27,7 +27,7 @@ def main():
                 ms = min(fn(pose0, nlo.Options(max_iterations=iters, **never))["device_ms"] for _ in range(7))
                 us = ms / iters * 1e3
                 print("%s n=%9d  %8.2f us/iter  %7.2f Gpoints/s  %6.1f GB/s" %
-                      (kind, n, us, n / us / 1e3, n * 120 / us / 1e3))
+                      (kind, n, us, n / us / 1e3, n * 96 / us / 1e3))
         pr.close()
     X, px, K = syn.pnp_problem(50000, 1003)
     pr = nlo.ReprojProblem(ctx, capacity=len(X)); pr.upload(X, px, K)
