@@ -28,14 +28,8 @@ class ReprojectionErrorMinimizerCuda : public ReprojectionErrorMinimizer {
     // 5 doubles per correspondence)
     points_.resize(3 * correspondences.size());
     pixels_.resize(2 * correspondences.size());
-    for (size_t i = 0; i < correspondences.size(); ++i) {
-      const Correspondence& c = correspondences[i];
-      points_[3 * i] = c.local_point(0);
-      points_[3 * i + 1] = c.local_point(1);
-      points_[3 * i + 2] = c.local_point(2);
-      pixels_[2 * i] = c.matched_pixel(0);
-      pixels_[2 * i + 1] = c.matched_pixel(1);
-    }
+    FlattenCorrespondences(correspondences.data(), correspondences.size(), points_.data(),
+                           pixels_.data());
     const double K[6] = {camera_intrinsics.fx, camera_intrinsics.fy, camera_intrinsics.cx,
                          camera_intrinsics.cy, camera_intrinsics.inv_fx, camera_intrinsics.inv_fy};
     int rc = nlo_reproj_upload(session_.ctx(), session_.problem(), n, points_.data(), pixels_.data(), K);

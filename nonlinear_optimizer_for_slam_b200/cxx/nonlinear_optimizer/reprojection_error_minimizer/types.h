@@ -3,6 +3,8 @@
 #ifndef NONLINEAR_OPTIMIZER_REPROJECTION_ERROR_MINIMIZER_TYPES_H_
 #define NONLINEAR_OPTIMIZER_REPROJECTION_ERROR_MINIMIZER_TYPES_H_
 
+#include <cstddef>
+
 #include "nonlinear_optimizer/types.h"
 
 namespace nonlinear_optimizer {
@@ -24,6 +26,31 @@ struct Correspondence {
   Vec3 local_point{Vec3::Zero()};    // 3-D point in the reference frame
   Vec2 matched_pixel{Vec2::Zero()};  // its observation in the query image
 };
+
+// Fills every field of CameraIntrinsics, the reciprocals included, from the four pinhole numbers.
+inline CameraIntrinsics MakeCameraIntrinsics(double fx, double fy, double cx, double cy, int width,
+                                             int height) {
+  CameraIntrinsics k;
+  k.fx = fx;
+  k.fy = fy;
+  k.cx = cx;
+  k.cy = cy;
+  k.inv_fx = 1.0 / fx;
+  k.inv_fy = 1.0 / fy;
+  k.width = width;
+  k.height = height;
+  return k;
+}
+
+// Splits an array of correspondences into the two flat arrays nlo_reproj_upload takes
+// (xyz triples and uv pairs); `points` and `pixels` must hold 3 * n and 2 * n doubles.
+inline void FlattenCorrespondences(const Correspondence* records, std::size_t n, double* points,
+                                   double* pixels) {
+  for (std::size_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) points[3 * i + k] = records[i].local_point(k);
+    for (int k = 0; k < 2; ++k) pixels[2 * i + k] = records[i].matched_pixel(k);
+  }
+}
 
 }  // namespace reprojection_error_minimizer
 }  // namespace nonlinear_optimizer
