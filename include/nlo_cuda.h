@@ -232,6 +232,20 @@ NLO_API int nlo_ndt_map_create(nlo_context* ctx, const double grid_origin[3], co
  * eigenvector signs; here each eigenvector's largest component is made positive). */
 NLO_API int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size,
                       int v_not_transposed, nlo_ndt_map** map);
+/* nlo_ndt_map_build keeps a dense grid over the points' bounding box and switches to the voxel
+ * hash by itself when that box has more than 2^28 voxels; nlo_ndt_map_build_hashed always builds
+ * the sparse form.  The reference holds its map in a std::unordered_map keyed by the voxel indices
+ * (:282-294); the device form is an open-addressing table (linear probing, at most half full) over
+ * the occupied voxels only, so memory follows the occupancy rather than the bounding box.  Matching
+ * against either form returns the same correspondences. */
+NLO_API int nlo_ndt_map_build_hashed(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size,
+                             int v_not_transposed, nlo_ndt_map** map);
+/* *hashed = 1 for the sparse form; *cells = rows of the tables nlo_ndt_map_download fills (grid
+ * cells when dense, hash slots when sparse). */
+NLO_API int nlo_ndt_map_layout(nlo_context* ctx, const nlo_ndt_map* map, int32_t* hashed, int64_t* cells);
+/* Sparse maps only: the key of every slot, x | y << 21 | z << 42 with voxel indices relative to
+ * grid_origin (nlo_ndt_map_info), or UINT64_MAX for a free slot. */
+NLO_API int nlo_ndt_map_download_keys(nlo_context* ctx, const nlo_ndt_map* map, uint64_t* slot_keys);
 /* dims/origin/voxel/cells of a map; then the tables (arrays sized from the first call). */
 NLO_API int nlo_ndt_map_info(nlo_context* ctx, const nlo_ndt_map* map, double grid_origin[3],
                      int32_t grid_dims[3], double* voxel_size, int64_t* valid_cells);

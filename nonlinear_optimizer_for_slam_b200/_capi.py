@@ -86,6 +86,10 @@ _SIGNATURES = {
                                           c_double_p, c_uint8_p, ctypes.POINTER(_VP)]),
     "nlo_ndt_map_build": (ctypes.c_int, [_VP, ctypes.c_int64, _VP, ctypes.c_double, ctypes.c_int,
                                          ctypes.POINTER(_VP)]),
+    "nlo_ndt_map_build_hashed": (ctypes.c_int, [_VP, ctypes.c_int64, _VP, ctypes.c_double, ctypes.c_int,
+                                                ctypes.POINTER(_VP)]),
+    "nlo_ndt_map_layout": (ctypes.c_int, [_VP, _VP, c_int32_p, c_int64_p]),
+    "nlo_ndt_map_download_keys": (ctypes.c_int, [_VP, _VP, _VP]),
     "nlo_ndt_map_info": (ctypes.c_int, [_VP, _VP, c_double_p, c_int32_p, c_double_p, c_int64_p]),
     "nlo_ndt_map_download": (ctypes.c_int, [_VP, _VP, c_double_p, c_double_p, c_uint8_p]),
     "nlo_ndt_map_destroy": (ctypes.c_int, [_VP, _VP]),

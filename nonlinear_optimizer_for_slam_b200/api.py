@@ -324,10 +324,12 @@ class ReprojProblem(_Problem):
 
 
 class NdtMap:
-    """Dense-voxel-grid NDT map on the device (UpdateNdtMap of the reference's test mains,
-    mahalanobis_distance_minimizer/tests/simple_optimization_test.cc:236-280)."""
+    """NDT map on the device (UpdateNdtMap of the reference's test mains,
+    mahalanobis_distance_minimizer/tests/simple_optimization_test.cc:236-280): a dense voxel grid
+    over the bounding box, or -- `hashed=True`, and by itself when the box has more than 2^28
+    voxels -- a voxel hash over the occupied voxels only (the reference's unordered_map, :282-294)."""
 
-    def __init__(self, ctx, grid=None, points=None, voxel=None, v_not_transposed=False):
+    def __init__(self, ctx, grid=None, points=None, voxel=None, v_not_transposed=False, hashed=False):
         self.ctx = ctx
         self._lib = ctx._lib
         self._h = ctypes.c_void_p()
@@ -340,9 +342,16 @@ class NdtMap:
                 _dp(mean), _dp(sq), valid.ctypes.data_as(_capi.c_uint8_p), ctypes.byref(self._h)))
         else:
             pts = _f64(points)
-            ctx._check(self._lib.nlo_ndt_map_build(ctx._h, pts.size // 3, pts.ctypes.data,
-                                                   float(voxel), int(v_not_transposed),
-                                                   ctypes.byref(self._h)))
+            build = self._lib.nlo_ndt_map_build_hashed if hashed else self._lib.nlo_ndt_map_build
+            ctx._check(build(ctx._h, pts.size // 3, pts.ctypes.data, float(voxel),
+                             int(v_not_transposed), ctypes.byref(self._h)))
+
+    def layout(self):
+        """(hashed, rows of the downloaded tables)."""
+        hashed = ctypes.c_int32(0); cells = ctypes.c_int64(0)
+        self.ctx._check(self._lib.nlo_ndt_map_layout(self.ctx._h, self._h, ctypes.byref(hashed),
+                                                     ctypes.byref(cells)))
+        return bool(hashed.value), cells.value
 
     def to_grid(self):
         origin = np.zeros(3); dims = np.zeros(3, dtype=np.int32)
@@ -350,12 +359,18 @@ class NdtMap:
         self.ctx._check(self._lib.nlo_ndt_map_info(self.ctx._h, self._h, _dp(origin),
                                                    dims.ctypes.data_as(_capi.c_int32_p),
                                                    ctypes.byref(voxel), ctypes.byref(nvalid)))
-        cells = int(dims.astype(np.int64).prod())
+        hashed, cells = self.layout()
         mean = np.zeros((cells, 3)); sq = np.zeros((cells, 9)); valid = np.zeros(cells, dtype=np.uint8)
         self.ctx._check(self._lib.nlo_ndt_map_download(self.ctx._h, self._h, _dp(mean), _dp(sq),
                                                        valid.ctypes.data_as(_capi.c_uint8_p)))
-        return {"origin": origin, "dims": dims, "voxel": voxel.value, "mean": mean,
-                "sqrt_info": sq, "valid": valid, "valid_cells": nvalid.value}
+        out = {"origin": origin, "dims": dims, "voxel": voxel.value, "mean": mean,
+               "sqrt_info": sq, "valid": valid, "valid_cells": nvalid.value, "hashed": hashed}
+        if hashed:
+            # rows are hash slots; keys = x | y << 21 | z << 42 (voxel indices from origin), all ones = free
+            keys = np.zeros(cells, dtype=np.uint64)
+            self.ctx._check(self._lib.nlo_ndt_map_download_keys(self.ctx._h, self._h, keys.ctypes.data))
+            out["keys"] = keys
+        return out
 
     def close(self):
         if getattr(self, "_h", None) and self.ctx._h:

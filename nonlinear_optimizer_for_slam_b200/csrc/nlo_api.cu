@@ -146,6 +146,9 @@ struct nlo_ndt_map {
   double* d_mean = nullptr;          // [cells][3]
   double* d_sqrt_info = nullptr;     // [cells][9] row-major
   unsigned char* d_valid = nullptr;  // [cells]
+  // sparse map: cells = slots of the voxel hash, dims = bounding box in voxels
+  unsigned long long* d_keys = nullptr;  // [cells], kHashEmpty = free slot
+  long long hash_mask = 0;
 };
 
 struct nlo_scan {
@@ -996,17 +999,33 @@ int nlo_reproj_solve_batched(nlo_context* ctx, nlo_problem* pr, const nlo_solve_
 // ---- NDT map / scan / matcher / outer registration loop ----
 namespace {
 
-int AllocMap(nlo_context* ctx, const double origin[3], const int32_t dims[3], double voxel, nlo_ndt_map** out) {
+constexpr int64_t kMaxMapCells = 1LL << 28;  // dense cells, or occupied voxels of a hashed map
+
+// hash_slots == 0: dense grid of dims cells; otherwise a voxel hash with that many slots (2^k).
+int AllocMap(nlo_context* ctx, const double origin[3], const int32_t dims[3], double voxel, int64_t hash_slots,
+             nlo_ndt_map** out) {
   if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || !(voxel > 0.0)) return Fail(ctx, NLO_EINVAL, "bad grid");
-  const int64_t cells = static_cast<int64_t>(dims[0]) * dims[1] * dims[2];
-  if (cells > (1LL << 28)) return Fail(ctx, NLO_EINVAL, "dense grid too large (> 2^28 cells)");
+  int64_t cells = hash_slots;
+  if (hash_slots == 0) {
+    // the product cannot overflow: each factor is first checked against the limit
+    if (dims[0] > kMaxMapCells || dims[1] > kMaxMapCells || dims[2] > kMaxMapCells ||
+        static_cast<int64_t>(dims[0]) * dims[1] > kMaxMapCells ||
+        static_cast<int64_t>(dims[0]) * dims[1] * dims[2] > kMaxMapCells)
+      return Fail(ctx, NLO_EINVAL, "dense grid too large (> 2^28 cells); build a hashed map");
+    cells = static_cast<int64_t>(dims[0]) * dims[1] * dims[2];
+  } else {
+    for (int k = 0; k < 3; ++k)
+      if (dims[k] > (1 << kHashAxisBits)) return Fail(ctx, NLO_EINVAL, "map spans more than 2^21 voxels on an axis");
+  }
   nlo_ndt_map* m = new nlo_ndt_map();
   for (int k = 0; k < 3; ++k) { m->origin[k] = origin[k]; m->dims[k] = dims[k]; }
   m->voxel = voxel;
   m->cells = cells;
+  m->hash_mask = hash_slots ? hash_slots - 1 : 0;
   if (cudaMalloc(&m->d_mean, cells * 3 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&m->d_sqrt_info, cells * 9 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&m->d_valid, cells) != cudaSuccess) {
+      cudaMalloc(&m->d_valid, cells) != cudaSuccess ||
+      (hash_slots && cudaMalloc(&m->d_keys, cells * sizeof(unsigned long long)) != cudaSuccess)) {
     nlo_ndt_map_destroy(ctx, m);
     return Fail(ctx, NLO_ENOMEM, "cudaMalloc(map) failed");
   }
@@ -1030,6 +1049,8 @@ int MatchInto(nlo_context* ctx, const nlo_scan* scan, const nlo_ndt_map* map, co
   mp.cell_mean = map->d_mean;
   mp.cell_sqrt_info = map->d_sqrt_info;
   mp.cell_valid = map->d_valid;
+  mp.keys = map->d_keys;
+  mp.hash_mask = map->hash_mask;
   mp.matched = d_matched;
   if (d_matched) NLO_CUDA(ctx, cudaMemsetAsync(d_matched, 0, sizeof(unsigned long long), ctx->stream));
   NLO_CUDA(ctx, LaunchMatchNdt(mp, ctx->stream));
@@ -1067,7 +1088,7 @@ int nlo_ndt_map_create(nlo_context* ctx, const double grid_origin[3], const int3
     return Fail(ctx, NLO_EINVAL, "null argument");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   nlo_ndt_map* m = nullptr;
-  int rc = AllocMap(ctx, grid_origin, grid_dims, voxel_size, &m);
+  int rc = AllocMap(ctx, grid_origin, grid_dims, voxel_size, 0, &m);
   if (rc != NLO_OK) return rc;
   cudaError_t e = cudaMemcpyAsync(m->d_mean, cell_mean, m->cells * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_sqrt_info, cell_sqrt_info, m->cells * 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
@@ -1081,8 +1102,17 @@ int nlo_ndt_map_create(nlo_context* ctx, const double grid_origin[3], const int3
   return NLO_OK;
 }
 
-int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size, int v_not_transposed,
-                      nlo_ndt_map** map) {
+namespace {
+
+int64_t NextPow2(int64_t v) {
+  int64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// layout: 0 dense, 1 hashed, 2 dense unless the bounding box has more than kMaxMapCells voxels
+int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size, int v_not_transposed,
+             int layout, nlo_ndt_map** map) {
   if (ctx == nullptr || map == nullptr || points_xyz == nullptr || n <= 0 || !(voxel_size > 0.0))
     return Fail(ctx, NLO_EINVAL, "bad argument");
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1102,13 +1132,45 @@ int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, dou
   int32_t dims[3];
   double origin[3];
   int kmin[3];
+  double box_cells = 1.0;
   for (int k = 0; k < 3; ++k) {
+    const int64_t span = static_cast<int64_t>(hb[3 + k]) - hb[k] + 1;
+    if (span > (1LL << 30)) return Fail(ctx, NLO_EINVAL, "points span more than 2^30 voxels on an axis");
     kmin[k] = hb[k];
-    dims[k] = hb[3 + k] - hb[k] + 1;
+    dims[k] = static_cast<int32_t>(span);
     origin[k] = hb[k] * voxel_size;
+    box_cells *= static_cast<double>(span);
   }
+  const bool hashed = layout == 1 || (layout == 2 && box_cells > static_cast<double>(kMaxMapCells));
+
+  int64_t slots = 0;
+  if (hashed) {
+    for (int k = 0; k < 3; ++k)
+      if (dims[k] > (1 << kHashAxisBits)) return Fail(ctx, NLO_EINVAL, "map spans more than 2^21 voxels on an axis");
+    // pass 1: distinct occupied voxels, through a scratch key table of >= 2 n slots
+    const int64_t scratch_slots = NextPow2(std::max<int64_t>(2 * n, 1024));
+    unsigned long long* d_scratch = nullptr;
+    if (cudaMalloc(&d_scratch, (scratch_slots + 1) * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaGetLastError();
+      return Fail(ctx, NLO_ENOMEM, "cudaMalloc(voxel hash scratch) failed");
+    }
+    unsigned long long* d_distinct = d_scratch + scratch_slots;
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0xff, scratch_slots * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_distinct, 0, sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess)
+      e = LaunchMapCountVoxels(d_xyz, n, inv, kmin, d_scratch, scratch_slots - 1, d_distinct, ctx->stream);
+    unsigned long long distinct = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->host_small, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_scratch);
+    if (e != cudaSuccess) return Fail(ctx, NLO_ECUDA, std::string("map build (voxel count): ") + cudaGetErrorString(e));
+    memcpy(&distinct, ctx->host_small, sizeof(distinct));
+    if (static_cast<int64_t>(distinct) > kMaxMapCells) return Fail(ctx, NLO_EINVAL, "more than 2^28 occupied voxels");
+    slots = NextPow2(std::max<int64_t>(2 * static_cast<int64_t>(distinct), 1024));
+  }
+
   nlo_ndt_map* m = nullptr;
-  rc = AllocMap(ctx, origin, dims, voxel_size, &m);
+  rc = AllocMap(ctx, origin, dims, voxel_size, slots, &m);
   if (rc != NLO_OK) return rc;
   int* d_count = nullptr;
   double* d_sums = nullptr;
@@ -1117,12 +1179,14 @@ int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, dou
   if (e == cudaSuccess) e = cudaMalloc(&d_sums, m->cells * 9 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, m->cells * sizeof(int), ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, m->cells * 9 * sizeof(double), ctx->stream);
+  if (e == cudaSuccess && hashed) e = cudaMemsetAsync(m->d_keys, 0xff, m->cells * sizeof(unsigned long long), ctx->stream);
   if (e == cudaSuccess) {
     MapAccumParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.xyz = d_xyz; ap.n = n; ap.inv_voxel = inv;
     for (int k = 0; k < 3; ++k) { ap.kmin[k] = kmin[k]; ap.dims[k] = dims[k]; }
     ap.count = d_count; ap.sums = d_sums;
+    ap.keys = m->d_keys; ap.hash_mask = m->hash_mask;
     e = LaunchMapAccumulate(ap, ctx->stream);
   }
   if (e == cudaSuccess)
@@ -1131,9 +1195,38 @@ int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, dou
   cleanup();
   if (e != cudaSuccess) {
     nlo_ndt_map_destroy(ctx, m);
-    return Fail(ctx, NLO_ECUDA, std::string("map build: ") + cudaGetErrorString(e));
+    return Fail(ctx, e == cudaErrorMemoryAllocation ? NLO_ENOMEM : NLO_ECUDA,
+                std::string("map build: ") + cudaGetErrorString(e));
   }
   *map = m;
+  return NLO_OK;
+}
+
+}  // namespace
+
+int nlo_ndt_map_build(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size, int v_not_transposed,
+                      nlo_ndt_map** map) {
+  return BuildMap(ctx, n, points_xyz, voxel_size, v_not_transposed, 2, map);
+}
+
+int nlo_ndt_map_build_hashed(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel_size,
+                             int v_not_transposed, nlo_ndt_map** map) {
+  return BuildMap(ctx, n, points_xyz, voxel_size, v_not_transposed, 1, map);
+}
+
+int nlo_ndt_map_layout(nlo_context* ctx, const nlo_ndt_map* map, int32_t* hashed, int64_t* cells) {
+  if (ctx == nullptr || map == nullptr) return Fail(ctx, NLO_EINVAL, "null argument");
+  if (hashed) *hashed = map->d_keys != nullptr ? 1 : 0;
+  if (cells) *cells = map->cells;
+  return NLO_OK;
+}
+
+int nlo_ndt_map_download_keys(nlo_context* ctx, const nlo_ndt_map* map, uint64_t* slot_keys) {
+  if (ctx == nullptr || map == nullptr || slot_keys == nullptr) return Fail(ctx, NLO_EINVAL, "null argument");
+  if (map->d_keys == nullptr) return Fail(ctx, NLO_EINVAL, "not a hashed map");
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NLO_CUDA(ctx, cudaMemcpy(slot_keys, map->d_keys, map->cells * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return NLO_OK;
 }
 
@@ -1174,6 +1267,7 @@ int nlo_ndt_map_destroy(nlo_context* ctx, nlo_ndt_map* map) {
   cudaFree(map->d_mean);
   cudaFree(map->d_sqrt_info);
   cudaFree(map->d_valid);
+  cudaFree(map->d_keys);
   delete map;
   return NLO_OK;
 }

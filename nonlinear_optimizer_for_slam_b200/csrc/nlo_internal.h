@@ -162,11 +162,21 @@ struct MatchParams {
   const double* cell_sqrt_info;
   const unsigned char* cell_valid;
   unsigned long long* matched;  // device counter of real (non-empty) correspondences
+  const unsigned long long* keys;  // hashed map: slot keys (nullptr = dense grid, cell = linear index)
+  long long hash_mask;             // slots - 1 (slots is a power of two)
 };
 cudaError_t LaunchMatchNdt(const MatchParams& p, cudaStream_t stream);
 cudaError_t LaunchPackScan(const double* xyz, int64_t n, double* const planes[3], cudaStream_t stream);
 
-// Device NDT map builder (UpdateNdtMap of the reference's test mains) on a dense voxel grid.
+// Voxel hash of the sparse map: the reference keeps its NDT map in a std::unordered_map keyed by
+// a pairing of the voxel indices (tests/simple_optimization_test.cc:282-294); on the device the
+// table is open-addressing with linear probing over 64-bit keys x | y << 21 | z << 42 (indices
+// relative to the map's lowest voxel), at most half full.
+constexpr unsigned long long kHashEmpty = ~0ull;
+constexpr int kHashAxisBits = 21;
+
+// Device NDT map builder (UpdateNdtMap of the reference's test mains) on a dense voxel grid or,
+// when `keys` is set, on the voxel hash.
 struct MapAccumParams {
   const double* xyz;  // interleaved points
   int64_t n;
@@ -175,7 +185,14 @@ struct MapAccumParams {
   int dims[3];
   int* count;       // [cells]
   double* sums;     // [cells][9]: sum xyz (3) | moment xx xy xz yy yz zz (6)
+  unsigned long long* keys;  // hashed: [slots], kHashEmpty-initialised; cells = slots
+  long long hash_mask;
 };
+// Inserts every point's voxel key into `keys` (scratch table, >= 2 n slots) and counts the
+// distinct voxels, so that the final table can be sized from the occupancy instead of from n.
+cudaError_t LaunchMapCountVoxels(const double* xyz, int64_t n, double inv_voxel, const int kmin[3],
+                                 unsigned long long* keys, long long hash_mask, unsigned long long* distinct,
+                                 cudaStream_t stream);
 cudaError_t LaunchMapBounds(const double* xyz, int64_t n, double inv_voxel, int* bounds6, cudaStream_t stream);
 cudaError_t LaunchMapAccumulate(const MapAccumParams& p, cudaStream_t stream);
 cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,

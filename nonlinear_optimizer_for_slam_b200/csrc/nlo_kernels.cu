@@ -1049,11 +1049,54 @@ cudaError_t LaunchGenerateNdt(const GenerateParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ voxel hash
+__device__ __forceinline__ unsigned long long VoxelHashKey(int x, int y, int z) {
+  return static_cast<unsigned long long>(x) | (static_cast<unsigned long long>(y) << kHashAxisBits) |
+         (static_cast<unsigned long long>(z) << (2 * kHashAxisBits));
+}
+__device__ __forceinline__ long long VoxelHashHome(unsigned long long key, long long mask) {
+  key ^= key >> 30; key *= 0xbf58476d1ce4e5b9ull;
+  key ^= key >> 27; key *= 0x94d049bb133111ebull;
+  key ^= key >> 31;
+  return static_cast<long long>(key) & mask;
+}
+// Slot of `key`, claiming an empty one on first sight.  *fresh (nullable) = this call claimed it.
+__device__ __forceinline__ long long VoxelHashInsert(unsigned long long* keys, long long mask, unsigned long long key,
+                                                     bool* fresh) {
+  long long s = VoxelHashHome(key, mask);
+  while (true) {
+    const unsigned long long seen = keys[s];
+    if (seen == key) { if (fresh) *fresh = false; return s; }
+    if (seen == kHashEmpty) {
+      const unsigned long long prev = atomicCAS(keys + s, kHashEmpty, key);
+      if (prev == kHashEmpty) { if (fresh) *fresh = true; return s; }
+      if (prev == key) { if (fresh) *fresh = false; return s; }
+    }
+    s = (s + 1) & mask;
+  }
+}
+// Slot of `key`, or -1.  Terminates because the table is never more than half full.
+__device__ __forceinline__ long long VoxelHashFind(const unsigned long long* __restrict__ keys, long long mask,
+                                                   unsigned long long key) {
+  long long s = VoxelHashHome(key, mask);
+  while (true) {
+    const unsigned long long seen = keys[s];
+    if (seen == key) return s;
+    if (seen == kHashEmpty) return -1;
+    s = (s + 1) & mask;
+  }
+}
+// floor(v) as a voxel index, saturated so that far-away points cannot overflow the int cast.
+__device__ __forceinline__ int VoxelIndex(double v) {
+  return static_cast<int>(fmin(fmax(floor(v), -1073741824.0), 1073741824.0));
+}
+
 // ------------------------------------------------------------------ device NDT matcher
 // Restates MatchPointCloud (mahalanobis_distance_minimizer/tests/simple_optimization_test.cc:296-342):
 // warp the point by the pose, take the (at most) two nearest valid cell means within the search
 // radius (flann radiusSearch with L2_Simple: squared distance < radius), emit one correspondence
 // per hit carrying the cell's mean and sqrt_information.  Instead of a KD-tree the dense voxel grid
+// (or the voxel hash of a sparse map, probed once per neighbouring voxel in the same z, y, x order)
 // is scanned `reach` cells around the point (a mean lies inside its own voxel, so every mean within
 // the radius is visited).  A missing neighbour becomes a zero-information record (exact zero
 // contribution), which keeps the output a fixed 2 x n layout with no compaction pass.
@@ -1065,9 +1108,9 @@ __global__ void match_ndt_kernel(const MatchParams m) {
     const double wx = m.R[0] * lx + m.R[1] * ly + m.R[2] * lz + m.t[0];
     const double wy = m.R[3] * lx + m.R[4] * ly + m.R[5] * lz + m.t[1];
     const double wz = m.R[6] * lx + m.R[7] * ly + m.R[8] * lz + m.t[2];
-    const int cx = static_cast<int>(floor((wx - m.origin[0]) * m.inv_voxel));
-    const int cy = static_cast<int>(floor((wy - m.origin[1]) * m.inv_voxel));
-    const int cz = static_cast<int>(floor((wz - m.origin[2]) * m.inv_voxel));
+    const int cx = VoxelIndex((wx - m.origin[0]) * m.inv_voxel);
+    const int cy = VoxelIndex((wy - m.origin[1]) * m.inv_voxel);
+    const int cz = VoxelIndex((wz - m.origin[2]) * m.inv_voxel);
     int best[2] = {-1, -1};
     double best_d2[2] = {m.radius2, m.radius2};
     for (int oz = -m.reach; oz <= m.reach; ++oz) {
@@ -1079,7 +1122,13 @@ __global__ void match_ndt_kernel(const MatchParams m) {
         for (int ox = -m.reach; ox <= m.reach; ++ox) {
           const int x = cx + ox;
           if (x < 0 || x >= m.dims[0]) continue;
-          const int c = (z * m.dims[1] + y) * m.dims[0] + x;
+          int c;
+          if (m.keys != nullptr) {
+            c = static_cast<int>(VoxelHashFind(m.keys, m.hash_mask, VoxelHashKey(x, y, z)));
+            if (c < 0) continue;
+          } else {
+            c = (z * m.dims[1] + y) * m.dims[0] + x;
+          }
           if (!m.cell_valid[c]) continue;
           const double ex = wx - m.cell_mean[3 * c], ey = wy - m.cell_mean[3 * c + 1],
                        ez = wz - m.cell_mean[3 * c + 2];
@@ -1164,13 +1213,32 @@ __global__ void map_accumulate_kernel(const MapAccumParams m) {
     const int kx = static_cast<int>(floor(x * m.inv_voxel)) - m.kmin[0];
     const int ky = static_cast<int>(floor(y * m.inv_voxel)) - m.kmin[1];
     const int kz = static_cast<int>(floor(z * m.inv_voxel)) - m.kmin[2];
-    const int64_t c = (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
+    const int64_t c = m.keys != nullptr
+                          ? VoxelHashInsert(m.keys, m.hash_mask, VoxelHashKey(kx, ky, kz), nullptr)
+                          : (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
     atomicAdd(m.count + c, 1);
     double* s = m.sums + 9 * c;
     atomicAdd(s + 0, x); atomicAdd(s + 1, y); atomicAdd(s + 2, z);
     atomicAdd(s + 3, x * x); atomicAdd(s + 4, x * y); atomicAdd(s + 5, x * z);
     atomicAdd(s + 6, y * y); atomicAdd(s + 7, y * z); atomicAdd(s + 8, z * z);
   }
+}
+
+__global__ void map_count_voxels_kernel(const double* __restrict__ xyz, int64_t n, double inv_voxel, int kx0, int ky0,
+                                        int kz0, unsigned long long* keys, long long mask,
+                                        unsigned long long* distinct) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  unsigned long long fresh_here = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int kx = static_cast<int>(floor(xyz[3 * i] * inv_voxel)) - kx0;
+    const int ky = static_cast<int>(floor(xyz[3 * i + 1] * inv_voxel)) - ky0;
+    const int kz = static_cast<int>(floor(xyz[3 * i + 2] * inv_voxel)) - kz0;
+    bool fresh = false;
+    VoxelHashInsert(keys, mask, VoxelHashKey(kx, ky, kz), &fresh);
+    fresh_here += fresh ? 1 : 0;
+  }
+  for (int off = 16; off > 0; off >>= 1) fresh_here += __shfl_xor_sync(0xffffffffu, fresh_here, off);
+  if ((threadIdx.x & 31) == 0 && fresh_here) atomicAdd(distinct, fresh_here);
 }
 
 // Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (row-major a[9]); eigenvalues ascending in
@@ -1269,6 +1337,14 @@ cudaError_t LaunchMapBounds(const double* xyz, int64_t n, double inv_voxel, int*
 cudaError_t LaunchMapAccumulate(const MapAccumParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   map_accumulate_kernel<<<GridFor(p.n, 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t LaunchMapCountVoxels(const double* xyz, int64_t n, double inv_voxel, const int kmin[3],
+                                 unsigned long long* keys, long long hash_mask, unsigned long long* distinct,
+                                 cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  map_count_voxels_kernel<<<GridFor(n, 256), 256, 0, stream>>>(xyz, n, inv_voxel, kmin[0], kmin[1], kmin[2], keys,
+                                                               hash_mask, distinct);
   return cudaGetLastError();
 }
 cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,

@@ -37,15 +37,18 @@ class NdtRegistrationCuda {
   void SetLossFunction(const std::shared_ptr<LossFunction>& loss_function) { loss_function_ = loss_function; }
 
   // UpdateNdtMap on the device.  reference_literal_sqrt_information selects the reference's
-  // `diag * V` form (:275-276) instead of `diag * V^T`.
+  // `diag * V` form (:275-276) instead of `diag * V^T`.  voxel_hash keeps only the occupied voxels
+  // in a device hash table (the reference's unordered_map, :282-294) instead of a dense grid over
+  // the bounding box; maps whose box exceeds 2^28 voxels take that form by themselves.
   bool BuildMap(const std::vector<Vec3>& points, double voxel_resolution,
-                bool reference_literal_sqrt_information = false) {
+                bool reference_literal_sqrt_information = false, bool voxel_hash = false) {
     if (!session_.EnsureContext()) return false;
     Flatten(points);
     if (map_ != nullptr) nlo_ndt_map_destroy(session_.ctx(), map_);
     map_ = nullptr;
-    const int rc = nlo_ndt_map_build(session_.ctx(), static_cast<int64_t>(points.size()), flat_.data(),
-                                     voxel_resolution, reference_literal_sqrt_information ? 1 : 0, &map_);
+    const auto build = voxel_hash ? nlo_ndt_map_build_hashed : nlo_ndt_map_build;
+    const int rc = build(session_.ctx(), static_cast<int64_t>(points.size()), flat_.data(), voxel_resolution,
+                         reference_literal_sqrt_information ? 1 : 0, &map_);
     return rc == NLO_OK ? true : session_.Report("nlo_ndt_map_build", rc);
   }
 

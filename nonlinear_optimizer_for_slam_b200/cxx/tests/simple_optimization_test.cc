@@ -344,6 +344,15 @@ void TestDeviceRegistration(bool planar) {
   if (!planar) CHECK_NEAR(PoseData(pose)[14], t[14], 2e-3);
   CHECK_NEAR(YawOf(pose), YawOf(true_pose), 1e-3);
   CHECK_TRUE(reg.last_result().outer_iterations >= 2 && reg.last_result().outer_iterations <= 10);
+
+  // the same registration against the voxel-hash form of the map: same correspondences, so the
+  // same rounds and the same pose up to the rounding of the map's atomic sums
+  const int dense_outer = reg.last_result().outer_iterations;
+  CHECK_TRUE(reg.BuildMap(global, 1.0, /*reference_literal_sqrt_information=*/false, /*voxel_hash=*/true));
+  Pose hashed_pose = Pose::Identity();
+  CHECK_TRUE(reg.Register(options, &hashed_pose, planar));
+  CHECK_TRUE(reg.last_result().outer_iterations == dense_outer);
+  for (int k = 0; k < 16; ++k) CHECK_NEAR(PoseData(hashed_pose)[k], PoseData(pose)[k], 1e-8);
 }
 
 }  // namespace

@@ -120,3 +120,101 @@ def test_map_build_matches_numpy(ctx, nlo, voxel):
     np.testing.assert_allclose(np.linalg.norm(quirk["sqrt_info"][v].reshape(-1, 3, 3), axis=2),
                                np.linalg.norm(Sg, axis=2), rtol=1e-7)
     ndt_map.close()
+
+
+def decode_voxel_keys(keys):
+    """x | y << 21 | z << 42 (include/nlo_cuda.h, nlo_ndt_map_download_keys)."""
+    mask = np.uint64((1 << 21) - 1)
+    return ((keys & mask).astype(np.int64), ((keys >> np.uint64(21)) & mask).astype(np.int64),
+            ((keys >> np.uint64(42)) & mask).astype(np.int64))
+
+
+@pytest.mark.parametrize("voxel", [1.0, 0.5])
+def test_hashed_map_holds_the_dense_map(ctx, nlo, voxel):
+    """The voxel hash (the reference's unordered_map, simple_optimization_test.cc:282-294) holds
+    exactly the occupied voxels of the dense grid, with the same NDT per voxel."""
+    points = syn.room_points()
+    dense = nlo.NdtMap(ctx, points=points, voxel=voxel).to_grid()
+    sparse_map = nlo.NdtMap(ctx, points=points, voxel=voxel, hashed=True)
+    sparse = sparse_map.to_grid()
+    assert sparse["hashed"] and not dense["hashed"]
+    np.testing.assert_array_equal(sparse["dims"], dense["dims"])
+    np.testing.assert_allclose(sparse["origin"], dense["origin"])
+    assert sparse["valid_cells"] == dense["valid_cells"]
+    used = sparse["keys"] != np.uint64(0xFFFFFFFFFFFFFFFF)
+    slots = len(sparse["keys"])
+    assert slots & (slots - 1) == 0 and 2 * used.sum() <= slots
+    # occupied voxels = voxels that hold at least one point
+    k = np.floor(points / voxel).astype(np.int64)
+    k -= k.min(axis=0)
+    dx, dy, dz = (int(v) for v in dense["dims"])
+    occupied = np.unique((k[:, 2] * dy + k[:, 1]) * dx + k[:, 0])
+    x, y, z = decode_voxel_keys(sparse["keys"][used])
+    cell = (z * dy + y) * dx + x
+    np.testing.assert_array_equal(np.sort(cell), occupied)
+    np.testing.assert_array_equal(sparse["valid"][used], dense["valid"][cell])
+    assert not sparse["valid"][~used].any()
+    # sums are accumulated with atomics in both builds, so compare to rounding, not to the bit
+    np.testing.assert_allclose(sparse["mean"][used], dense["mean"][cell], rtol=0, atol=1e-11)
+    Is = syn.information6(sparse["sqrt_info"][used]); Id = syn.information6(dense["sqrt_info"][cell])
+    np.testing.assert_allclose(Is, Id, rtol=1e-8, atol=1e-8 * np.abs(Id).max())
+    sparse_map.close()
+
+
+def test_hashed_match_equals_dense_match(ctx, nlo):
+    points = syn.room_points()
+    rng = np.random.default_rng(17)
+    world = syn.room_surface_samples(30000, rng, 0.02)
+    Tinv = np.linalg.inv(syn.CFG1_TRUE)
+    local = world @ Tinv[:3, :3].T + Tinv[:3, 3]
+    # a few points far outside the map and one absurdly far away: no neighbours, no overflow
+    local[:3] = [[500.0, 0, 0], [0, -700.0, 3], [1e15, -1e15, 1e15]]
+    T = syn.yaw_pose([0.03, -0.02, 0.05], 0.02)
+    scan = nlo.Scan(ctx, local)
+    n = len(local)
+    got = []
+    for hashed in (False, True):
+        ndt_map = nlo.NdtMap(ctx, points=points, voxel=1.0, hashed=hashed)
+        prob = nlo.NdtProblem(ctx, capacity=2 * n)
+        matched = scan.match(ndt_map, syn.to_pose16(T), prob)
+        got.append((matched,) + tuple(prob.download(0, 2 * n)))
+        prob.close(); ndt_map.close()
+    assert got[0][0] == got[1][0] > n
+    np.testing.assert_array_equal(got[0][1], got[1][1])
+    np.testing.assert_allclose(got[0][2], got[1][2], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(got[0][3], got[1][3], rtol=1e-8, atol=1e-8 * np.abs(got[0][3]).max())
+    for j in range(2):
+        assert not got[1][3][j * n:j * n + 3].any()
+    scan.close()
+
+
+def test_sparse_map_past_the_dense_limit_registers(ctx, nlo):
+    """Two rooms 30 km apart: the bounding box has ~2e9 voxels (a dense grid is refused above
+    2^28), the hash holds ~2 x the occupied ones; registration in the far room still lands."""
+    shift = np.array([30000.0, 12000.0, 0.0])
+    far_room = syn.room_points() + shift
+    near_room = far_room - shift     # exact, so both rooms fall into voxels the same way
+    one = nlo.NdtMap(ctx, points=near_room, voxel=1.0)
+    valid_one = one.to_grid()["valid_cells"]
+    one.close()
+    ndt_map = nlo.NdtMap(ctx, points=np.concatenate([near_room, far_room]), voxel=1.0)   # plain build
+    hashed, slots = ndt_map.layout()
+    assert hashed and slots <= 4096
+    g = ndt_map.to_grid()
+    assert np.prod(g["dims"].astype(np.float64)) > 2 ** 28
+    assert g["valid_cells"] == 2 * valid_one
+    rng = np.random.default_rng(9)
+    world = syn.room_surface_samples(20000, rng, 0.01)
+    Tinv = np.linalg.inv(syn.CFG1_TRUE)
+    local = world @ Tinv[:3, :3].T + Tinv[:3, 3]
+    ctx.set_loss(1, [1.0, 1.0])
+    scan = nlo.Scan(ctx, local)
+    near = scan.register(ndt_map, nlo.identity_pose())
+    T0 = np.eye(4); T0[:3, 3] = shift
+    far = scan.register(ndt_map, syn.to_pose16(T0))
+    Rn, tn = nlo.pose_to_Rt(near["pose"]); Rf, tf = nlo.pose_to_Rt(far["pose"])
+    np.testing.assert_allclose(tn, syn.CFG1_TRUE[:3, 3], atol=1e-2)
+    np.testing.assert_allclose(tf - shift, tn, atol=1e-6)
+    assert rotation_angle(Rn, Rf) < 1e-6
+    assert far["matched"] == near["matched"]
+    scan.close(); ndt_map.close()
