@@ -1180,17 +1180,15 @@ int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel
   if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, m->cells * sizeof(int), ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, m->cells * 9 * sizeof(double), ctx->stream);
   if (e == cudaSuccess && hashed) e = cudaMemsetAsync(m->d_keys, 0xff, m->cells * sizeof(unsigned long long), ctx->stream);
-  if (e == cudaSuccess) {
-    MapAccumParams ap;
-    memset(&ap, 0, sizeof(ap));
-    ap.xyz = d_xyz; ap.n = n; ap.inv_voxel = inv;
-    for (int k = 0; k < 3; ++k) { ap.kmin[k] = kmin[k]; ap.dims[k] = dims[k]; }
-    ap.count = d_count; ap.sums = d_sums;
-    ap.keys = m->d_keys; ap.hash_mask = m->hash_mask;
-    e = LaunchMapAccumulate(ap, ctx->stream);
-  }
+  MapAccumParams ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.xyz = d_xyz; ap.n = n; ap.inv_voxel = inv; ap.voxel = voxel_size;
+  for (int k = 0; k < 3; ++k) { ap.kmin[k] = kmin[k]; ap.dims[k] = dims[k]; }
+  ap.count = d_count; ap.sums = d_sums;
+  ap.keys = m->d_keys; ap.hash_mask = m->hash_mask;
+  if (e == cudaSuccess) e = LaunchMapAccumulate(ap, ctx->stream);
   if (e == cudaSuccess)
-    e = LaunchMapFinalize(d_count, d_sums, m->cells, v_not_transposed, m->d_mean, m->d_sqrt_info, m->d_valid, ctx->stream);
+    e = LaunchMapFinalize(ap, m->cells, v_not_transposed, m->d_mean, m->d_sqrt_info, m->d_valid, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cleanup();
   if (e != cudaSuccess) {

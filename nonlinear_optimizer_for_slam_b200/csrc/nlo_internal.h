@@ -183,8 +183,9 @@ struct MapAccumParams {
   double inv_voxel;
   int kmin[3];
   int dims[3];
+  double voxel;
   int* count;       // [cells]
-  double* sums;     // [cells][9]: sum xyz (3) | moment xx xy xz yy yz zz (6)
+  double* sums;     // [cells][9]: sum d (3) | moment d d^T: xx xy xz yy yz zz (6), d = p - voxel centre
   unsigned long long* keys;  // hashed: [slots], kHashEmpty-initialised; cells = slots
   long long hash_mask;
 };
@@ -195,9 +196,9 @@ cudaError_t LaunchMapCountVoxels(const double* xyz, int64_t n, double inv_voxel,
                                  cudaStream_t stream);
 cudaError_t LaunchMapBounds(const double* xyz, int64_t n, double inv_voxel, int* bounds6, cudaStream_t stream);
 cudaError_t LaunchMapAccumulate(const MapAccumParams& p, cudaStream_t stream);
-cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,
-                              double* cell_mean, double* cell_sqrt_info, unsigned char* cell_valid,
-                              cudaStream_t stream);
+// `p` as given to LaunchMapAccumulate (the voxel centres are rebuilt from kmin / dims / keys).
+cudaError_t LaunchMapFinalize(const MapAccumParams& p, int64_t cells, int v_not_transposed, double* cell_mean,
+                              double* cell_sqrt_info, unsigned char* cell_valid, cudaStream_t stream);
 
 }  // namespace nlo
 

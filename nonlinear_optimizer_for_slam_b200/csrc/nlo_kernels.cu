@@ -464,15 +464,18 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           const double* base = partial_base + j;
           double s = 0.0;
           int g = l8;
-          // loads are issued 8 at a time (independent addresses), the adds keep the fixed order
-          for (; g + 56 < grid_x; g += 64) {
-            double v[8];
+          // loads are issued 16 at a time (independent addresses, the tail predicated so that it
+          // costs one round trip instead of one per element); the adds keep the fixed order
+          for (; g < grid_x; g += 128) {
+            double v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + static_cast<size_t>(g + 8 * u) * NACC);
+            for (int u = 0; u < 16; ++u) {
+              const int c = g + 8 * u;
+              v[u] = c < grid_x ? __ldcg(base + static_cast<size_t>(c) * NACC) : 0.0;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s += v[u];
+            for (int u = 0; u < 16; ++u) s += v[u];
           }
-          for (; g < grid_x; g += 8) s += __ldcg(base + static_cast<size_t>(g) * NACC);
           sm.warp_sums[l8][j] = s;
         }
         __syncthreads();
@@ -1206,13 +1209,19 @@ __global__ void map_bounds_kernel(const double* __restrict__ xyz, int64_t n, dou
   }
 }
 
+// Sums are taken about the voxel centre: the covariance is shift-invariant, and the reference's
+// raw-moment form (moment / n - mean mean^T, :255-259) loses 2 log10(|p| / voxel) digits to
+// cancellation for maps far from the origin.
 __global__ void map_accumulate_kernel(const MapAccumParams m) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += stride) {
-    const double x = m.xyz[3 * i], y = m.xyz[3 * i + 1], z = m.xyz[3 * i + 2];
-    const int kx = static_cast<int>(floor(x * m.inv_voxel)) - m.kmin[0];
-    const int ky = static_cast<int>(floor(y * m.inv_voxel)) - m.kmin[1];
-    const int kz = static_cast<int>(floor(z * m.inv_voxel)) - m.kmin[2];
+    const int ax = static_cast<int>(floor(m.xyz[3 * i] * m.inv_voxel));
+    const int ay = static_cast<int>(floor(m.xyz[3 * i + 1] * m.inv_voxel));
+    const int az = static_cast<int>(floor(m.xyz[3 * i + 2] * m.inv_voxel));
+    const double x = m.xyz[3 * i] - (ax + 0.5) * m.voxel;
+    const double y = m.xyz[3 * i + 1] - (ay + 0.5) * m.voxel;
+    const double z = m.xyz[3 * i + 2] - (az + 0.5) * m.voxel;
+    const int kx = ax - m.kmin[0], ky = ay - m.kmin[1], kz = az - m.kmin[2];
     const int64_t c = m.keys != nullptr
                           ? VoxelHashInsert(m.keys, m.hash_mask, VoxelHashKey(kx, ky, kz), nullptr)
                           : (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
@@ -1289,26 +1298,43 @@ __device__ inline void SymmetricEigen3(const double* a_in, double* w, double* V)
   }
 }
 
-__global__ void map_finalize_kernel(const int* __restrict__ count, const double* __restrict__ sums, int64_t cells,
-                                    int v_not_transposed, double* cell_mean, double* cell_sqrt_info,
-                                    unsigned char* cell_valid) {
+__global__ void map_finalize_kernel(const MapAccumParams m, int64_t cells, int v_not_transposed, double* cell_mean,
+                                    double* cell_sqrt_info, unsigned char* cell_valid) {
   const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (c >= cells) return;
   double mean[3] = {0, 0, 0}, S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned char valid = 0;
-  const int n = count[c];
+  const int n = m.count[c];
   if (n >= 5) {  // :250-253
+    // voxel indices of this cell, from the slot key or the linear index
+    int64_t idx[3];
+    if (m.keys != nullptr) {
+      const unsigned long long key = m.keys[c];
+      const unsigned long long axis_mask = (1ull << kHashAxisBits) - 1ull;
+      idx[0] = static_cast<int64_t>(key & axis_mask);
+      idx[1] = static_cast<int64_t>((key >> kHashAxisBits) & axis_mask);
+      idx[2] = static_cast<int64_t>((key >> (2 * kHashAxisBits)) & axis_mask);
+    } else {
+      idx[0] = c % m.dims[0];
+      idx[1] = (c / m.dims[0]) % m.dims[1];
+      idx[2] = c / (static_cast<int64_t>(m.dims[0]) * m.dims[1]);
+    }
     const double inv_n = 1.0 / n;
-    const double* s = sums + 9 * c;
-    for (int a = 0; a < 3; ++a) mean[a] = s[a] * inv_n;
-    // moment starts at Identity (types.h:14): cov = (I + sum p p^T) / n - mean mean^T
+    const double* s = m.sums + 9 * c;
+    double off[3];  // mean relative to the voxel centre
+    for (int a = 0; a < 3; ++a) {
+      off[a] = s[a] * inv_n;
+      mean[a] = (static_cast<double>(idx[a] + m.kmin[a]) + 0.5) * m.voxel + off[a];
+    }
+    // moment starts at Identity (types.h:14): cov = (I + sum p p^T) / n - mean mean^T, evaluated
+    // about the voxel centre (same value, no cancellation)
     double cov[9];
-    cov[0] = (s[3] + 1.0) * inv_n - mean[0] * mean[0];
-    cov[1] = cov[3] = s[4] * inv_n - mean[0] * mean[1];
-    cov[2] = cov[6] = s[5] * inv_n - mean[0] * mean[2];
-    cov[4] = (s[6] + 1.0) * inv_n - mean[1] * mean[1];
-    cov[5] = cov[7] = s[7] * inv_n - mean[1] * mean[2];
-    cov[8] = (s[8] + 1.0) * inv_n - mean[2] * mean[2];
+    cov[0] = (s[3] + 1.0) * inv_n - off[0] * off[0];
+    cov[1] = cov[3] = s[4] * inv_n - off[0] * off[1];
+    cov[2] = cov[6] = s[5] * inv_n - off[0] * off[2];
+    cov[4] = (s[6] + 1.0) * inv_n - off[1] * off[1];
+    cov[5] = cov[7] = s[7] * inv_n - off[1] * off[2];
+    cov[8] = (s[8] + 1.0) * inv_n - off[2] * off[2];
     double w[3], V[9];
     SymmetricEigen3(cov, w, V);
     if (w[2] >= 0.01) {  // :263
@@ -1347,12 +1373,11 @@ cudaError_t LaunchMapCountVoxels(const double* xyz, int64_t n, double inv_voxel,
                                                                hash_mask, distinct);
   return cudaGetLastError();
 }
-cudaError_t LaunchMapFinalize(const int* count, const double* sums, int64_t cells, int v_not_transposed,
-                              double* cell_mean, double* cell_sqrt_info, unsigned char* cell_valid,
-                              cudaStream_t stream) {
+cudaError_t LaunchMapFinalize(const MapAccumParams& p, int64_t cells, int v_not_transposed, double* cell_mean,
+                              double* cell_sqrt_info, unsigned char* cell_valid, cudaStream_t stream) {
   if (cells <= 0) return cudaSuccess;
   map_finalize_kernel<<<static_cast<int>((cells + 127) / 128), 128, 0, stream>>>(
-      count, sums, cells, v_not_transposed, cell_mean, cell_sqrt_info, cell_valid);
+      p, cells, v_not_transposed, cell_mean, cell_sqrt_info, cell_valid);
   return cudaGetLastError();
 }
 
