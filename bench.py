@@ -566,7 +566,7 @@ def measure_small_configs(nlo, syn, ctx):
                                  "gpoints_s": len(p) * r / 1e9}
     pr.close()
 
-    # opt-in throughput mode: the cfg4 scan stored as float (60 B per correspondence), fp64 math
+    # opt-in throughput mode: the cfg4 scan stored as float (48 B per correspondence), fp64 math
     n32 = TOTAL_POINTS
     try:
         pr = nlo.NdtProblem(ctx, capacity=n32, storage="f32")
@@ -575,9 +575,9 @@ def measure_small_configs(nlo, syn, ctx):
         r, us = rate(lambda k: pr.solve6(pose0, nlo.Options(max_iterations=k, **never)), iters=20, reps=3)
         out["cfg4_f32_storage_optin"] = {
             "gpoints_s": n32 * r / 1e9, "us_per_iteration": us, "points": n32,
-            "hbm_gbs": n32 * 60 * r / 1e9, "bytes_per_correspondence": 60,
-            "note": "correspondences stored as float, arithmetic in fp64; equals the fp64 path on "
-                    "float-rounded inputs (tests), ~1e-7 relative input quantisation vs the parity mode"}
+            "hbm_gbs": n32 * 48 * r / 1e9, "bytes_per_correspondence": 48,
+            "note": "records (point, mean, S^T S) stored as float, arithmetic in fp64; equals the fp64 "
+                    "path on the float-rounded records (tests), ~1e-7 relative quantisation vs the parity mode"}
         # the same mode end to end from pinned FLOAT host arrays (half the PCIe bytes), 16M points
         n_e = 16 * 1024 * 1024
         arr, handle = nlo.host_alloc(n_e * 60)

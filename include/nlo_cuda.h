@@ -102,11 +102,12 @@ NLO_API int nlo_host_free(void* ptr);
 /* ---- NDT / Mahalanobis correspondences (types.h:11-26) ---- */
 /* One problem of up to `capacity` correspondences. */
 NLO_API int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
-/* Same, with the correspondences STORED as float on the device (60 instead of 120 bytes each) and
- * all arithmetic still in fp64 -- the storage the reference's float SIMD minimizers use
- * (..._analytic_simd.cc:19-28, SOAData).  Results equal the fp64 path run on float-rounded inputs;
- * against the unrounded double inputs they differ by the input quantisation (~1e-7 relative), so
- * this is an opt-in throughput mode, not the parity mode.  Supported: upload, generate, download,
+/* Same, with the correspondences STORED as float on the device (48 instead of 96 bytes each: point,
+ * mean and the 6 unique entries of S^T S, formed in fp64 and rounded once) and all arithmetic still
+ * in fp64 -- float storage as in the reference's SIMD minimizers (..._analytic_simd.cc:19-28,
+ * SOAData).  Results equal the fp64 path run on the float-rounded records (nlo_ndt_download
+ * returns them); against the unrounded double inputs they differ by that quantisation (~1e-7
+ * relative), so this is an opt-in throughput mode, not the parity mode.  Supported: upload, generate, download,
  * ndt6/ndt3 assemble and solve (single problem, also sharded over GPUs). */
 NLO_API int nlo_ndt_create_f32(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
 /* Upload into an fp32-storage problem from FLOAT host arrays (same record order as nlo_ndt_upload):

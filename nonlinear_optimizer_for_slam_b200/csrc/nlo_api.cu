@@ -200,7 +200,7 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
   nlo_problem* pr = new nlo_problem();
   pr->family = family;
-  pr->num_planes = (family == 0) ? (f32 ? kNdtPlanes : kNdtPlanesF64) : kReprojPlanes;
+  pr->num_planes = (family == 0) ? kNdtPlanes : kReprojPlanes;
   pr->num_problems = num_problems;
   pr->batched = batched;
   pr->f32 = f32;

@@ -12,9 +12,9 @@ enum Kind : int { kNdt6 = 0, kNdt3 = 1, kReproj = 2 };
 constexpr int kTile = 256;            // correspondences per pipeline stage = consumer threads
 constexpr int kConsumerWarps = kTile / 32;
 constexpr int kThreads = kTile;       // thread 0 doubles as the TMA producer
-constexpr int kNdtPlanes = 15;        // fp32 storage (and array bound): x y z | mx my mz | s00 s01 s02 s10 .. s22
-constexpr int kNdtPlanesF64 = 12;     // fp64 storage: x y z | mx my mz | L00 L01 L02 L11 L12 L22 with L = S^T S,
-                                      // formed once at ingest (both NDT minimizers need S only through S^T S)
+constexpr int kNdtPlanes = 12;        // x y z | mx my mz | L00 L01 L02 L11 L12 L22 with L = S^T S, formed once
+                                      // at ingest (both NDT minimizers need S only through S^T S); stored as
+                                      // double (96 B per correspondence) or, opt-in, as float (48 B)
 constexpr int kReprojPlanes = 5;      // X Y Z | u v
 constexpr int kAcc6 = 28;             // 21 H + 6 g + cost
 constexpr int kAcc3 = 10;             // 6 H + 3 g + cost

@@ -119,20 +119,20 @@ struct KindTraits<kReproj> {
 // Planes of one correspondence for a kind and a storage type.
 template <int KIND, typename ST>
 __host__ __device__ constexpr int PlanesOf() {
-  return KIND == kReproj ? kReprojPlanes : (sizeof(ST) == 8 ? kNdtPlanesF64 : kNdtPlanes);
+  return KIND == kReproj ? kReprojPlanes : kNdtPlanes;
 }
 
-// ST = storage type of the planes in HBM and in the stages: double (parity mode, 120 B per NDT
-// correspondence) or float (fp32 storage, fp64 math: 60 B; twice the stages fit the same smem).
+// ST = storage type of the planes in HBM and in the stages: double (parity mode, 96 B per NDT
+// correspondence) or float (fp32 storage, fp64 math: 48 B; twice the stages fit the same smem).
 template <int KIND, typename ST>
 struct SmemLayout {
   using T = KindTraits<KIND>;
-  // bytes per stage: NDT fp64 24 KB (12 planes), NDT fp32 15 KB (15 planes), PnP 10 KB; two CTAs
-  // per SM share the 227 KB
+  // bytes per stage: NDT fp64 24 KB (12 planes), NDT fp32 12 KB, PnP 10 KB; two CTAs per SM share
+  // the 227 KB
 #ifndef NLO_NDT_STAGES
 #define NLO_NDT_STAGES 4
 #endif
-  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? NLO_NDT_STAGES : 6);
+  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? NLO_NDT_STAGES : 8);
   ST stages[kStages][PlanesOf<KIND, ST>()][kTile];
   double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
   double total[32];            // reduced (raw, then canonical) sums
@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = PlanesOf<KIND, ST>();
-  constexpr bool HAS_L = sizeof(ST) == 8;  // fp64 storage carries S^T S, fp32 storage carries S
   constexpr int MAX_STAGES = SmemLayout<KIND, ST>::kStages;
   // ring depth actually used (<= the stages allocated): chosen per launch shape by the host
   const int STAGES = (p.stage_depth > 0 && p.stage_depth < MAX_STAGES) ? p.stage_depth : MAX_STAGES;
@@ -327,9 +326,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
               (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
           const bool valid = (idx >= range.begin) && (idx < range.end);
           if (KIND == kNdt6)
-            Ndt6Point<LOSS, HAS_L>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
           else if (KIND == kNdt3)
-            Ndt3Point<LOSS, HAS_L>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
           else
             ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
         }
@@ -707,20 +706,14 @@ __device__ __forceinline__ ST* NdtElem(double* plane0, int k, int64_t i) {
   return reinterpret_cast<ST*>(plane0) + TiledOffset(PlanesOf<kNdt6, ST>(), i) + k * kTile;
 }
 
-// Stores the information part of an NDT record from its sqrt_information S (row-major):
-// fp64 storage keeps the 6 unique entries of L = S^T S, fp32 storage keeps the 9 entries of S.
+// Stores the information part of an NDT record from its sqrt_information S (row-major): the 6
+// unique entries of L = S^T S, formed in fp64 and rounded once to the storage type.
 template <typename ST>
 __device__ __forceinline__ void StoreNdtInformation(double* plane0, int64_t i, const double* S) {
-  if (sizeof(ST) == 8) {
-    const double L[6] = {S[0] * S[0] + S[3] * S[3] + S[6] * S[6], S[0] * S[1] + S[3] * S[4] + S[6] * S[7],
-                         S[0] * S[2] + S[3] * S[5] + S[6] * S[8], S[1] * S[1] + S[4] * S[4] + S[7] * S[7],
-                         S[1] * S[2] + S[4] * S[5] + S[7] * S[8], S[2] * S[2] + S[5] * S[5] + S[8] * S[8]};
+  double L[6];
+  InformationFromSqrt(S, L);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) *NdtElem<ST>(plane0, 6 + k, i) = static_cast<ST>(L[k]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) *NdtElem<ST>(plane0, 6 + k, i) = static_cast<ST>(S[k]);
-  }
+  for (int k = 0; k < 6; ++k) *NdtElem<ST>(plane0, 6 + k, i) = static_cast<ST>(L[k]);
 }
 
 template <typename ST>
@@ -749,8 +742,10 @@ __global__ void pack_ndt_from_float_kernel(const float* __restrict__ point, cons
     for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], k, i) = point[3 * i + k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], 3 + k, i) = mean[3 * i + k];
+    double S[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) *NdtElem<float>(planes.p[0], 6 + k, i) = sqrt_info[9 * i + k];
+    for (int k = 0; k < 9; ++k) S[k] = static_cast<double>(sqrt_info[9 * i + k]);
+    StoreNdtInformation<float>(planes.p[0], i, S);
   }
 }
 
@@ -810,14 +805,7 @@ __global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, 
     for (int k = 0; k < 3; ++k) point[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], k, i));
     for (int k = 0; k < 3; ++k) mean[3 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 3 + k, i));
     // third output: the 6 unique entries of the information matrix S^T S (00 01 02 11 12 22)
-    if (sizeof(ST) == 8) {
-      for (int k = 0; k < 6; ++k) sqrt_info[6 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 6 + k, i));
-    } else {
-      double v[15];
-      for (int k = 6; k < 15; ++k) v[k] = static_cast<double>(*NdtElem<ST>(planes.p[0], k, i));
-      NdtInformation<false>(v, sqrt_info[6 * o], sqrt_info[6 * o + 1], sqrt_info[6 * o + 2], sqrt_info[6 * o + 3],
-                            sqrt_info[6 * o + 4], sqrt_info[6 * o + 5]);
-    }
+    for (int k = 0; k < 6; ++k) sqrt_info[6 * o + k] = static_cast<double>(*NdtElem<ST>(planes.p[0], 6 + k, i));
   }
 }
 

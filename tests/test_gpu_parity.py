@@ -528,33 +528,49 @@ def _f32_round(a):
     return np.asarray(a, dtype=np.float32).astype(np.float64)
 
 
+def _well_conditioned(S, floor=0.05):
+    """The same records with the singular values of every S raised to >= floor * the largest, so that
+    S^T S stays positive definite after rounding to float (the test rebuilds an S from it)."""
+    U, d, Vt = np.linalg.svd(np.asarray(S).reshape(-1, 3, 3))
+    d = np.maximum(d, floor * d[:, :1])
+    return np.einsum("nij,nj,njk->nik", U, d, Vt).reshape(-1, 9)
+
+
 @pytest.mark.parametrize("n", [1, 255, 4097, 70001])
-def test_f32_storage_equals_oracle_on_float_rounded_inputs(ctx, nlo, oracle, n):
-    """Opt-in throughput mode: correspondences stored as float, arithmetic in fp64.  It must equal
-    the double oracle evaluated on the float-rounded inputs to the normal parity bar, and deviate
-    from the unrounded inputs only by the input quantisation."""
+def test_f32_storage_equals_oracle_on_float_rounded_records(ctx, nlo, oracle, n):
+    """Opt-in throughput mode: records (point, mean, S^T S) stored as float, arithmetic in fp64.  It
+    must equal the double oracle evaluated on the float-rounded records to the normal parity bar."""
     rng = np.random.default_rng(500 + n)
     point, mean, S = syn.random_ndt_records(n, seed=900 + n)
+    S = _well_conditioned(S)
     pose16, R, t = _rand_pose(rng, nlo)
     prob = nlo.NdtProblem(ctx, capacity=n, storage="f32")
-    prob.upload(point, mean, S)
+    p64 = nlo.NdtProblem(ctx, capacity=n)
+    p64.upload(point, mean, S)
+    i64 = p64.download(0, n)[2]
+    p64.close()
+    prob.upload_f32(point, mean, S)           # float host arrays: S is rounded before S^T S is formed
+    p3, m3, i3 = prob.download(0, n)
+    np.testing.assert_array_equal(p3, _f32_round(point))
+    np.testing.assert_array_equal(m3, _f32_round(mean))
+    ref3 = syn.information6(_f32_round(S))
+    np.testing.assert_allclose(i3, ref3, rtol=2e-7, atol=2e-7 * np.abs(ref3).max())
+    prob.upload(point, mean, S)               # double host arrays: S^T S in fp64, rounded once
     p2, m2, i2 = prob.download(0, n)
     np.testing.assert_array_equal(p2, _f32_round(point))
-    np.testing.assert_allclose(i2, syn.information6(_f32_round(S)), rtol=1e-13, atol=1e-13 * np.abs(S).max() ** 2)
-    prob.upload_f32(point, mean, S)           # float host arrays give the same device contents
-    p3, m3, i3 = prob.download(0, n)
-    assert np.array_equal(p3, p2) and np.array_equal(m3, m2) and np.array_equal(i3, i2)
+    np.testing.assert_array_equal(m2, _f32_round(mean))
+    np.testing.assert_array_equal(i2, _f32_round(i64))
+    S2 = syn.sqrt_info_from_information6(i2)  # an S whose S^T S is the stored information
+    np.testing.assert_allclose(syn.information6(S2), i2, rtol=1e-13, atol=1e-13 * np.abs(i2).max())
     Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(R))
     for loss in [(0, None), (1, [1.0, 1.0]), (2, [1.0])]:
         ctx.set_loss(loss[0], loss[1])
         H, g, c = prob.assemble6(pose16)
-        Hr, gr, cr = oracle.ndt6_assemble(_f32_round(point), _f32_round(mean), _f32_round(S), Rq, t,
-                                          loss[0], loss[1], long_double=True)
+        Hr, gr, cr = oracle.ndt6_assemble(p2, m2, S2, Rq, t, loss[0], loss[1], long_double=True)
         assert_sums_close(H, g, c, Hr, gr, cr)
         H3, g3, c3 = prob.assemble3(syn.to_pose16(syn.yaw_pose([0.1, -0.1, 0.0], 0.05)))
         T = syn.yaw_pose([0.1, -0.1, 0.0], 0.05)
-        Hr3, gr3, cr3 = oracle.ndt3_assemble(_f32_round(point), _f32_round(mean), _f32_round(S), T[:2, :2],
-                                             T[:2, 3], loss[0], loss[1], long_double=True)
+        Hr3, gr3, cr3 = oracle.ndt3_assemble(p2, m2, S2, T[:2, :2], T[:2, 3], loss[0], loss[1], long_double=True)
         assert_sums_close(H3, g3, c3, Hr3, gr3, cr3)
     prob.close()
 
@@ -565,7 +581,8 @@ def test_f32_storage_solve_trajectory_and_quantisation_error(ctx, nlo, oracle):
     p32 = nlo.NdtProblem(ctx, capacity=len(point), storage="f32")
     p32.upload(point, mean, S)
     res = p32.solve6(nlo.identity_pose(), trace=True)
-    ref = oracle.ndt6_solve(_f32_round(point), _f32_round(mean), _f32_round(S), nlo.identity_pose(), 1, [1.0, 1.0])
+    pf, mf, inf = p32.download(0, len(point))
+    ref = oracle.ndt6_solve(pf, mf, syn.sqrt_info_from_information6(inf), nlo.identity_pose(), 1, [1.0, 1.0])
     _check_trajectory(res, ref, 36, nlo)
     # against the unrounded double problem: only the input quantisation (float eps ~ 6e-8) shows
     p64 = nlo.NdtProblem(ctx, capacity=len(point))
@@ -587,7 +604,6 @@ def test_f32_storage_solve_trajectory_and_quantisation_error(ctx, nlo, oracle):
     a = g32p.download(0, 5000); b = g64p.download(0, 5000)
     np.testing.assert_array_equal(a[0], _f32_round(b[0]))
     np.testing.assert_array_equal(a[1], _f32_round(b[1]))
-    # information of float-rounded S vs of S (entries that cancel to ~0 need an absolute scale)
-    np.testing.assert_allclose(a[2], b[2], rtol=1e-6, atol=1e-6 * np.abs(b[2]).max())
+    np.testing.assert_array_equal(a[2], _f32_round(b[2]))
     for pr in (p32, p64, g32p, g64p):
         pr.close()
