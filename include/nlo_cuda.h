@@ -23,8 +23,9 @@
  *     becomes 12 doubles (point 3, mean 3, the 6 unique entries of S^T S formed once at ingest).
  *   - H is the packed upper triangle in row-major order: 6-DoF 21 values
  *     (0,0),(0,1)..(0,5),(1,1)..(5,5); 3-DoF 6 values.  g is J^T W r (6 or 3).
- *   - a context owns one CUDA device + one stream; calls on one context are serialised by the
- *     caller (same contract as the reference minimizers: not re-entrant per instance).
+ *   - a context owns one CUDA device + one stream (nlo_context_create) or several devices of this
+ *     process (nlo_context_create_multi); calls on one context are serialised by the caller (same
+ *     contract as the reference minimizers: not re-entrant per instance).
  *   - there is no CPU fallback: without a usable CUDA device nlo_context_create fails.
  */
 #ifndef NLO_CUDA_H_
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NLO_ABI_VERSION 1
+#define NLO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NLO_API __attribute__((visibility("default")))
@@ -51,7 +52,8 @@ enum {
   NLO_ECUDA = -2,    /* CUDA runtime error (message in nlo_last_error) */
   NLO_ENOMEM = -3,   /* allocation failed */
   NLO_ECOMM = -4,    /* NCCL / peer-memory communicator error */
-  NLO_ENUMERIC = -5  /* non-finite H, g or step met during a solve */
+  NLO_ENUMERIC = -5, /* non-finite H, g or step met during a solve */
+  NLO_ETIMEOUT = -6  /* a grid-wide wait of the persistent iteration kernel expired (GPU shared / preempted) */
 };
 
 /* loss_function.h:20-77.  params: EXPONENTIAL {c1, c2}; HUBER {threshold}; CAUCHY {c}
@@ -86,7 +88,20 @@ typedef struct nlo_problem nlo_problem;
 
 /* ---- context ---- */
 NLO_API int nlo_abi_version(void);
+/* CUDA devices visible to this process (0 without a driver / GPU). */
+NLO_API int nlo_visible_device_count(void);
 NLO_API int nlo_context_create(int device, nlo_context** ctx);
+/* One context over `num_devices` (<= 8) devices of THIS process -- the reference splits the
+ * correspondence vector over its thread pool inside Solve (..._analytic.cc:59-73,104-119,
+ * ..._analytic_simd.cc:55-76); here the split is over B200s, behind the same calls.  A single problem is
+ * sharded by contiguous point range at upload / generate, every device runs the iteration kernel on
+ * its shard, the 28 (10) doubles are summed each iteration by the one-shot all-reduce over directly
+ * mapped peer memory (NVLink), and every device applies the identical step; the 3-DoF solve drops
+ * the last n mod 4 correspondences of the WHOLE list, as the reference.  A batched problem is
+ * partitioned by registration id, no exchange.  Every call of this header except nlo_comm_* works on
+ * such a context (maps, scans and nlo_ndt_register run on its first device). */
+NLO_API int nlo_context_create_multi(const int32_t* devices, int32_t num_devices, nlo_context** ctx);
+NLO_API int nlo_context_device_count(const nlo_context* ctx);
 NLO_API int nlo_context_destroy(nlo_context* ctx);
 NLO_API const char* nlo_last_error(const nlo_context* ctx);
 /* sm_count, and the grid (CTAs) a single-problem assembly launch uses */
@@ -127,6 +142,11 @@ NLO_API int nlo_ndt_upload(nlo_context* ctx, nlo_problem* problem, int64_t n, co
 NLO_API int nlo_ndt_upload_aos(nlo_context* ctx, nlo_problem* problem, int64_t n, const void* records,
                        size_t stride, size_t offset_point, size_t offset_mean,
                        size_t offset_sqrt_info, int sqrt_info_col_major);
+/* Wall time of the last nlo_*_upload* call on the context and the part of it the calling thread spent
+ * in the host-side gather (ms).  Uploads are chunked and pipelined: host threads gather the 15 (5) hot
+ * doubles of each record into a ring of pinned chunks while the previous chunk crosses PCIe and is
+ * repacked on the device; the caller's memory may be pageable; device staging is O(chunk). */
+NLO_API int nlo_ingest_stats(const nlo_context* ctx, double* total_ms, double* host_gather_ms);
 /* Device-side synthetic correspondences (bench / large-scale tests; no host copy):
  * point i = counter-based PRNG(seed, global_index_offset + i) on the surfaces of the 7x5x2.5 m
  * room of tests/simple_optimization_test.cc:170-204 expressed in the sensor frame of
@@ -151,6 +171,9 @@ NLO_API int nlo_ndt_generate_batched(nlo_context* ctx, nlo_problem* problem, uin
  * device keeps S only through S^T S, which is all both NDT minimizers use. */
 NLO_API int nlo_ndt_download(nlo_context* ctx, const nlo_problem* problem, int64_t begin, int64_t end,
                      double* point, double* mean, double* information);
+/* Same for registration `problem_index` of a batched problem (0 for a single one). */
+NLO_API int nlo_ndt_download_problem(nlo_context* ctx, const nlo_problem* problem, int32_t problem_index,
+                             int64_t begin, int64_t end, double* point, double* mean, double* information);
 
 /* ---- reprojection correspondences (reprojection_error_minimizer/types.h:14-28) ---- */
 NLO_API int nlo_reproj_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);
@@ -163,6 +186,12 @@ NLO_API int nlo_reproj_create_batched(nlo_context* ctx, int32_t num_problems, co
 NLO_API int nlo_reproj_upload(nlo_context* ctx, nlo_problem* problem, int64_t n,
                       const double* local_point, const double* pixel,
                       const double intrinsics[6]);
+
+/* Ingest the reference's AoS records in place (std::vector<Correspondence>::data(), types.h:14-17):
+ * byte offsets of local_point (3 doubles) and matched_pixel_point (2 doubles). */
+NLO_API int nlo_reproj_upload_aos(nlo_context* ctx, nlo_problem* problem, int64_t n, const void* records,
+                          size_t stride, size_t offset_local_point, size_t offset_pixel,
+                          const double intrinsics[6]);
 
 NLO_API int nlo_problem_destroy(nlo_context* ctx, nlo_problem* problem);
 NLO_API int64_t nlo_problem_size(const nlo_problem* problem);
@@ -285,7 +314,8 @@ NLO_API int nlo_ndt_register(nlo_context* ctx, const nlo_scan* scan, const nlo_n
                      int32_t max_outer, int32_t three_dof, double pose[16],
                      nlo_register_result* result);
 
-/* ---- multi-GPU (one process per GPU; a large scan sharded by point range) ----
+/* ---- multi-GPU, one process per GPU (a large scan sharded by point range; for several GPUs inside
+ * one process see nlo_context_create_multi) ----
  * With a communicator attached, every assemble/solve on the context sums its 28 (10 for 3-DoF)
  * partial doubles over all ranks each iteration and every rank applies the identical update.
  * NCCL flavour: rank 0 calls nlo_comm_unique_id and ships the 128 bytes to the others. */
@@ -295,6 +325,17 @@ NLO_API int nlo_comm_init_nccl(nlo_context* ctx, const uint8_t id[128], int32_t 
  * every rank exports a 64-byte handle, gathers all of them (rank order) and opens the peers. */
 NLO_API int nlo_comm_peer_export(nlo_context* ctx, uint8_t handle[64]);
 NLO_API int nlo_comm_peer_init(nlo_context* ctx, const uint8_t* handles, int32_t rank, int32_t nranks);
+/* This problem holds correspondences [global_begin, global_begin + n) of a scan of global_total that is
+ * sharded over ranks.  Only the planar solve needs to know: the reference drops the last
+ * global_total mod 4 correspondences of the WHOLE list (..._analytic_3dof.cc:33-36), so nlo_ndt3_solve
+ * cuts this shard at floor(global_total / 4) * 4 - global_begin instead of at floor(n / 4) * 4.
+ * global_total < 0 clears the setting.  (A multi-device context does this by itself.) */
+NLO_API int nlo_problem_set_global_range(nlo_context* ctx, nlo_problem* problem, int64_t global_begin,
+                                 int64_t global_total);
+/* suspended != 0: later assemble / solve calls behave as if no communicator were attached (this
+ * rank's own, un-reduced sums); 0 restores the collective.  Parity checks use it to compare the
+ * all-reduced sums with the per-rank ones. */
+NLO_API int nlo_comm_suspend(nlo_context* ctx, int32_t suspended);
 NLO_API int nlo_comm_destroy(nlo_context* ctx);
 
 #ifdef __cplusplus

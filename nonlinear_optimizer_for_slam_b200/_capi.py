@@ -34,7 +34,10 @@ _VP = ctypes.c_void_p
 # name -> (restype, argtypes); every symbol include/nlo_cuda.h declares
 _SIGNATURES = {
     "nlo_abi_version": (ctypes.c_int, []),
+    "nlo_visible_device_count": (ctypes.c_int, []),
     "nlo_context_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_VP)]),
+    "nlo_context_create_multi": (ctypes.c_int, [c_int32_p, ctypes.c_int32, ctypes.POINTER(_VP)]),
+    "nlo_context_device_count": (ctypes.c_int, [_VP]),
     "nlo_context_destroy": (ctypes.c_int, [_VP]),
     "nlo_last_error": (ctypes.c_char_p, [_VP]),
     "nlo_context_info": (ctypes.c_int, [_VP, c_int_p, c_int_p]),
@@ -59,6 +62,11 @@ _SIGNATURES = {
                                                 ctypes.c_double, c_double_p, c_double_p, c_uint8_p]),
     "nlo_ndt_download": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int64, c_double_p,
                                         c_double_p, c_double_p]),
+    "nlo_ndt_download_problem": (ctypes.c_int, [_VP, _VP, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                                c_double_p, c_double_p, c_double_p]),
+    "nlo_ingest_stats": (ctypes.c_int, [_VP, c_double_p, c_double_p]),
+    "nlo_reproj_upload_aos": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, ctypes.c_size_t,
+                                             ctypes.c_size_t, ctypes.c_size_t, c_double_p]),
     "nlo_reproj_create": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),
     "nlo_reproj_create_batched": (ctypes.c_int, [_VP, ctypes.c_int32, c_int64_p, ctypes.POINTER(_VP)]),
     "nlo_reproj_upload": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP, _VP, c_double_p]),
@@ -104,6 +112,8 @@ _SIGNATURES = {
     "nlo_comm_init_nccl": (ctypes.c_int, [_VP, c_uint8_p, ctypes.c_int32, ctypes.c_int32]),
     "nlo_comm_peer_export": (ctypes.c_int, [_VP, c_uint8_p]),
     "nlo_comm_peer_init": (ctypes.c_int, [_VP, c_uint8_p, ctypes.c_int32, ctypes.c_int32]),
+    "nlo_problem_set_global_range": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int64]),
+    "nlo_comm_suspend": (ctypes.c_int, [_VP, ctypes.c_int32]),
     "nlo_comm_destroy": (ctypes.c_int, [_VP]),
 }
 

@@ -59,14 +59,40 @@ class Options:
 
 
 class Context:
-    def __init__(self, device=0):
+    """One device (`device=k`), or several devices of this process (`devices=[...]`): a single
+    problem is then sharded by point range over them, a batched one by registration id
+    (nlo_context_create_multi)."""
+
+    def __init__(self, device=0, devices=None):
         self._lib = _capi.load()
         h = ctypes.c_void_p()
-        rc = self._lib.nlo_context_create(device, ctypes.byref(h))
-        if rc != 0:
-            raise NloError(rc, "nlo_context_create(device=%d) failed (no usable sm_100 GPU?)" % device)
+        if devices is not None:
+            arr = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self._lib.nlo_context_create_multi(arr.ctypes.data_as(_capi.c_int32_p), len(arr),
+                                                    ctypes.byref(h))
+            if rc != 0:
+                raise NloError(rc, "nlo_context_create_multi(%s) failed" % list(arr))
+            device = int(arr[0])
+        else:
+            rc = self._lib.nlo_context_create(device, ctypes.byref(h))
+            if rc != 0:
+                raise NloError(rc, "nlo_context_create(device=%d) failed (no usable sm_100 GPU?)" % device)
         self._h = h
         self.device = device
+
+    @property
+    def device_count(self):
+        return int(self._lib.nlo_context_device_count(self._h))
+
+    def ingest_stats(self):
+        """(wall ms, host gather ms) of the last upload on this context."""
+        t = ctypes.c_double(0); g = ctypes.c_double(0)
+        self._check(self._lib.nlo_ingest_stats(self._h, ctypes.byref(t), ctypes.byref(g)))
+        return t.value, g.value
+
+    def comm_suspend(self, suspended=True):
+        """Later assemble / solve calls use this rank's own, un-reduced sums (parity checks)."""
+        self._check(self._lib.nlo_comm_suspend(self._h, int(bool(suspended))))
 
     def _check(self, rc):
         if rc != 0:
@@ -142,6 +168,12 @@ class _Problem:
     @property
     def size(self):
         return int(self._lib.nlo_problem_size(self._h))
+
+    def set_global_range(self, global_begin, global_total):
+        """This problem is the shard [global_begin, ...) of a scan of global_total points spread over
+        ranks: the planar solve then drops the tail of the WHOLE list, as the reference."""
+        self.ctx._check(self._lib.nlo_problem_set_global_range(self.ctx._h, self._h, global_begin,
+                                                               global_total))
 
     def _assemble(self, fn, nh, ng, pose16, begin, end, problem_index):
         pose = _f64(pose16).reshape(16)
@@ -253,12 +285,13 @@ class NdtProblem(_Problem):
             dims.ctypes.data_as(_capi.c_int32_p), float(grid["voxel"]), _dp(mean), _dp(sq),
             valid.ctypes.data_as(_capi.c_uint8_p)))
 
-    def download(self, begin, end):
-        """point[n,3], mean[n,3], information[n,6] = unique entries (00 01 02 11 12 22) of S^T S."""
+    def download(self, begin, end, problem_index=0):
+        """point[n,3], mean[n,3], information[n,6] = unique entries (00 01 02 11 12 22) of S^T S
+        of correspondences [begin, end) (of registration `problem_index` for a batched problem)."""
         n = end - begin
         point = np.zeros((n, 3)); mean = np.zeros((n, 3)); info = np.zeros((n, 6))
-        self.ctx._check(self._lib.nlo_ndt_download(self.ctx._h, self._h, begin, end, _dp(point),
-                                                   _dp(mean), _dp(info)))
+        self.ctx._check(self._lib.nlo_ndt_download_problem(self.ctx._h, self._h, problem_index, begin,
+                                                           end, _dp(point), _dp(mean), _dp(info)))
         return point, mean, info
 
     def assemble6(self, pose16, begin=0, end=None, problem_index=0):
@@ -312,6 +345,12 @@ class ReprojProblem(_Problem):
         n = X.size // 3
         self.ctx._check(self._lib.nlo_reproj_upload(self.ctx._h, self._h, n, X.ctypes.data,
                                                     px.ctypes.data, _dp(K)))
+
+    def upload_aos(self, records, n, stride, off_point, off_pixel, intrinsics):
+        """The reference's 40-byte Correspondence records in place (types.h:14-17)."""
+        records = np.ascontiguousarray(records); K = _f64(intrinsics)
+        self.ctx._check(self._lib.nlo_reproj_upload_aos(self.ctx._h, self._h, n, records.ctypes.data,
+                                                        stride, off_point, off_pixel, _dp(K)))
 
     def assemble(self, pose16, begin=0, end=None):
         """reprojection_error_minimizer_analytic.cc:31-63."""

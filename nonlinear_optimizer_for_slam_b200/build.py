@@ -6,8 +6,8 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libnlo_cuda.so")
-SOURCES = ["nlo_kernels.cu", "nlo_api.cu"]
-HEADERS = ["nlo_internal.h", "nlo_device.cuh", os.path.join("..", "..", "include", "nlo_cuda.h")]
+SOURCES = ["nlo_kernels.cu", "nlo_api.cu", "nlo_ingest.cu", "nlo_map.cu", "nlo_multi.cu"]
+HEADERS = ["nlo_internal.h", "nlo_host.h", "nlo_device.cuh", os.path.join("..", "..", "include", "nlo_cuda.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -49,7 +49,7 @@ def build_cuda(force=False, verbose=False):
             print(out.decode())
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-ldl"]
+    link = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-ldl", "-lpthread"]
     subprocess.run(link, check=True)
     return LIB_PATH
 
@@ -71,6 +71,25 @@ def build_cxx_example(force=False):
            "-Wl,-rpath," + _PKG, "-Wl,-rpath,$ORIGIN/../.."]
     subprocess.run(cmd, check=True)
     return CXX_TEST_BIN
+
+
+CXX_BENCH_SRC = os.path.join(_PKG, "cxx", "bench", "dropin_bench.cc")
+CXX_BENCH_BIN = os.path.join(_PKG, "cxx", "bench", "dropin_bench")
+
+
+def build_cxx_bench(force=False):
+    """Compile the drop-in end-to-end benchmark (times ...Cuda::Solve on std::vector<Correspondence>)."""
+    build_cuda()
+    if (not force and os.path.exists(CXX_BENCH_BIN)
+            and os.path.getmtime(CXX_BENCH_BIN) >= os.path.getmtime(CXX_BENCH_SRC)
+            and os.path.getmtime(CXX_BENCH_BIN) >= os.path.getmtime(LIB_PATH)):
+        return CXX_BENCH_BIN
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread",
+           "-I", os.path.join(_PKG, "..", "include"), "-I", os.path.join(_PKG, "cxx"),
+           CXX_BENCH_SRC, "-o", CXX_BENCH_BIN, "-L", _PKG, "-lnlo_cuda",
+           "-Wl,-rpath," + _PKG, "-Wl,-rpath,$ORIGIN/../.."]
+    subprocess.run(cmd, check=True)
+    return CXX_BENCH_BIN
 
 
 if __name__ == "__main__":

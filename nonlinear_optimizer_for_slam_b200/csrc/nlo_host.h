@@ -1,0 +1,254 @@
+// nlo_host.h -- host-side structures shared by the translation units behind the C ABI
+// (nlo_api.cu: contexts, problems, assemble / solve, communicators; nlo_ingest.cu: host -> device
+// ingest; nlo_map.cu: NDT map, scan, matcher, outer registration loop; nlo_multi.cu: one context
+// spanning several devices of the process).  Nothing here is visible through include/nlo_cuda.h.
+#ifndef NLO_HOST_H_
+#define NLO_HOST_H_
+
+#include <array>
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/nlo_cuda.h"
+#include "nlo_internal.h"
+
+namespace nlo {
+
+// ---- NCCL through dlopen (no link-time dependency; the symbols are only needed multi-process) ----
+struct NcclUniqueId {
+  char internal[128];
+};
+typedef void* NcclComm;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+enum CommKind { kCommNone = 0, kCommNccl = 1, kCommPeer = 2 };
+
+constexpr size_t kPeerBufBytes = 2 * kMaxRanks * kPeerWords * sizeof(unsigned long long);
+constexpr int kInCtaTiles = 3;       // a registration this small runs its whole loop inside one CTA
+constexpr int kSmallDoubles = 8192;  // pinned + device scratch for poses / sums / results
+
+// Host -> device ingest pipeline of one context (nlo_ingest.cu): a ring of pinned chunks that host
+// threads fill (gather of the hot scalars out of the caller's records, or a plain copy out of
+// pageable arrays) while the previous chunk travels over PCIe and is repacked on the device.
+struct IngestRing {
+  static constexpr int kSlots = 3;
+  size_t chunk_bytes = 0;  // capacity of every slot (host and device)
+  unsigned char* host[kSlots] = {nullptr, nullptr, nullptr};   // pinned
+  unsigned char* device[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};      // device finished reading slot k
+  bool used[kSlots] = {false, false, false};
+};
+
+// A persistent worker thread (one per device of a multi-device context).
+class Worker {
+ public:
+  Worker();
+  ~Worker();
+  void Post(std::function<void()> job);
+  void Wait();
+
+ private:
+  void Loop();
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool has_job_ = false, busy_ = false, stop_ = false;
+  std::thread thread_;
+};
+
+}  // namespace nlo
+
+struct nlo_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  int grid_single = 0;
+  int loss_kind = NLO_LOSS_NONE;
+  double loss_params[2] = {0.0, 0.0};
+  std::string error;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+  double* host_small = nullptr;  // pinned
+  bool use_graph = true;
+  bool use_persistent = true;
+  int stage_depth = 0;            // NLO_STAGE_DEPTH: ring depth override (0 = per-shape default)
+  double l2_keep_mb = 0.0;        // NLO_L2_KEEP_MB: bytes of a re-read scan pinned in L2 (0 = off)
+  double l2_policy_min_mb = 0.0;  // only scans larger than this get an explicit policy
+  int grid_small = 0;             // CTAs of the persistent path for L2-resident problems
+  int cluster_size = 0;           // NLO_CLUSTER: CTAs per thread-block cluster of the persistent path (0 = default)
+  // communicator
+  int comm_kind = nlo::kCommNone;
+  bool comm_suspended = false;  // nlo_comm_suspend: calls behave as if no communicator were attached
+  bool comm_in_process = false; // peer buffers of the other devices are mapped directly (multi-device context)
+  int rank = 0, nranks = 1;
+  nlo::NcclApi nccl;
+  nlo::NcclComm nccl_comm = nullptr;
+  unsigned char* peer_buf = nullptr;  // local exchange buffer (exported over CUDA IPC / mapped by peers)
+  void* peer_opened[nlo::kMaxRanks] = {nullptr};
+  nlo::PeerComm peer{};
+  unsigned long long* d_peer_seq = nullptr;
+  int* d_peer_error = nullptr;
+  nlo_problem* reg_workspace = nullptr;  // correspondences of nlo_ndt_register: kept across scans,
+  int64_t reg_workspace_capacity = 0;    // grown on demand (no per-frame allocation)
+  unsigned long long* d_debug_times = nullptr;  // NLO_DEBUG_TIMES=1: [64][8] stamps of the last loop
+  int generation = 0;  // bumped whenever cached graphs become stale (loss / comm change)
+  // ingest pipeline
+  nlo::IngestRing ring;
+  int ingest_threads = 0;  // host threads one upload may use (NLO_INGEST_THREADS; 0 = decide per call)
+  double last_ingest_ms = 0.0, last_ingest_gather_ms = 0.0;  // wall time of the last upload / its host gather
+  // multi-device context (nlo_context_create_multi): this object is then only a dispatcher
+  std::vector<nlo_context*> subs;
+  std::vector<nlo::Worker*> workers;
+
+  bool IsMulti() const { return !subs.empty(); }
+  int EffectiveComm() const { return comm_suspended ? nlo::kCommNone : comm_kind; }
+};
+
+struct nlo_problem {
+  int family = 0;  // 0 NDT, 1 reprojection
+  int num_planes = 0;
+  int64_t capacity = 0;  // padded, per plane
+  int64_t n = 0;
+  int num_problems = 1;
+  bool batched = false;
+  bool f32 = false;  // planes stored as float (NDT, single problem only): fp32 storage, fp64 math
+  double* plane_block = nullptr;
+  double* planes[nlo::kNdtPlanes] = {nullptr};
+  std::vector<nlo::Range> h_ranges;
+  std::vector<int64_t> counts;
+  nlo::Range* d_ranges = nullptr;  // [num_problems + 1]; the last slot is the scratch range for assemble
+  nlo::State* d_states = nullptr;  // [num_problems + 1]
+  double* d_partials = nullptr;
+  unsigned int* d_tickets = nullptr;     // [num_problems + 1]
+  unsigned long long* d_sync = nullptr;  // [num_problems + 1][kSyncStride] persistent-path counter + LL state
+  double* d_sums = nullptr;              // [(num_problems + 1) * 32]
+  double* d_poses = nullptr;             // [(num_problems + 1) * 16]
+  double* d_results = nullptr;           // [(num_problems + 1) * 4]
+  double* d_trace = nullptr;
+  size_t trace_doubles = 0;
+  double intrinsics[6] = {0, 0, 0, 0, 0, 0};
+  std::map<std::array<int64_t, 10>, cudaGraphExec_t> graphs;
+  // 3-DoF solve of a shard of a larger scan: the reference drops the last n mod 4 correspondences of
+  // the WHOLE list (..._analytic_3dof.cc:33-36), so the owner of the shards fixes the end of every
+  // shard's range here (-1 = this problem is the whole list: floor(n / 4) * 4).
+  int64_t ndt3_end_override = -1;
+  // multi-device problem: one shard per device (point ranges for a single problem, problem-id
+  // ranges for a batched one); this object is then only a dispatcher
+  std::vector<nlo_problem*> shards;
+  std::vector<int64_t> shard_begin;  // [shards + 1]: first point (single) / first problem id (batched) of shard r
+};
+
+struct nlo_ndt_map {
+  nlo_context* owner = nullptr;  // the (sub-)context whose device holds the tables
+  double origin[3] = {0, 0, 0};
+  int dims[3] = {0, 0, 0};
+  double voxel = 0.0;
+  int64_t cells = 0;
+  double* d_mean = nullptr;          // [cells][3]
+  double* d_sqrt_info = nullptr;     // [cells][9] row-major
+  unsigned char* d_valid = nullptr;  // [cells]
+  // sparse map: cells = slots of the voxel hash, dims = bounding box in voxels
+  unsigned long long* d_keys = nullptr;  // [cells], kHashEmpty = free slot
+  long long hash_mask = 0;
+};
+
+struct nlo_scan {
+  int64_t n = 0;
+  double* block = nullptr;
+  double* planes[3] = {nullptr, nullptr, nullptr};
+  unsigned long long* d_matched = nullptr;
+};
+
+namespace nlo {
+
+int Fail(nlo_context* ctx, int code, const std::string& msg);
+
+#define NLO_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      return ::nlo::Fail((ctx), (_e == cudaErrorMemoryAllocation) ? NLO_ENOMEM : NLO_ECUDA, \
+                         std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    }                                                                                    \
+  } while (0)
+
+int EnsureStaging(nlo_context* ctx, size_t bytes);
+void DropGraphs(nlo_problem* pr);
+void PoseToRt(const double pose[16], double R[9], double t[3]);
+
+// nlo_api.cu (single-device implementations the multi-device dispatcher calls per shard)
+int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t* counts, bool batched,
+                  nlo_problem** out, bool f32 = false);
+int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index, const double pose[16],
+                 int64_t begin, int64_t end, double* H, int nh, double* g, int ng, double* cost);
+int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* options, double* poses,
+              nlo_solve_result* results, double* trace, bool batched_call);
+
+// nlo_ingest.cu
+int UploadNdt(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* point, const double* mean,
+              const double* sqrt_info);
+int UploadNdtF32(nlo_context* ctx, nlo_problem* pr, int64_t n, const float* point, const float* mean,
+                 const float* sqrt_info);
+int UploadNdtAos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
+                 size_t offset_point, size_t offset_mean, size_t offset_sqrt_info, int col_major);
+int UploadReproj(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* local_point, const double* pixel,
+                 const double intrinsics[6]);
+int UploadReprojAos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
+                    size_t offset_local_point, size_t offset_pixel, const double intrinsics[6]);
+int GenerateNdt(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t global_index_offset, double noise_sigma,
+                const double* true_poses, const double init_pose[16], const double grid_origin[3],
+                const int32_t grid_dims[3], double voxel_size, const double* cell_mean,
+                const double* cell_sqrt_info, const uint8_t* cell_valid, int64_t n_single);
+int DownloadNdt(nlo_context* ctx, const nlo_problem* pr, int32_t problem_index, int64_t begin, int64_t end,
+                double* point, double* mean, double* information);
+void FreeIngestRing(nlo_context* ctx);
+
+// nlo_multi.cu
+namespace multi {
+int CreateContext(const int* devices, int n, nlo_context** out);
+void DestroyContext(nlo_context* ctx);
+int SetLoss(nlo_context* ctx, int kind, const double params[2]);
+int Synchronize(nlo_context* ctx);
+int Create(nlo_context* ctx, int family, int num_problems, const int64_t* counts, bool batched, bool f32,
+           nlo_problem** out);
+int Destroy(nlo_context* ctx, nlo_problem* pr);
+int UploadNdt(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* point, const double* mean,
+              const double* sqrt_info);
+int UploadNdtF32(nlo_context* ctx, nlo_problem* pr, int64_t n, const float* point, const float* mean,
+                 const float* sqrt_info);
+int UploadNdtAos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
+                 size_t offset_point, size_t offset_mean, size_t offset_sqrt_info, int col_major);
+int UploadReproj(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* local_point, const double* pixel,
+                 const double intrinsics[6]);
+int UploadReprojAos(nlo_context* ctx, nlo_problem* pr, int64_t n, const void* records, size_t stride,
+                    size_t offset_local_point, size_t offset_pixel, const double intrinsics[6]);
+int Generate(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t global_index_offset, double noise_sigma,
+             const double* true_poses, const double init_pose[16], const double grid_origin[3],
+             const int32_t grid_dims[3], double voxel_size, const double* cell_mean, const double* cell_sqrt_info,
+             const uint8_t* cell_valid, int64_t n_single);
+int Download(nlo_context* ctx, const nlo_problem* pr, int32_t problem_index, int64_t begin, int64_t end,
+             double* point, double* mean, double* information);
+int Assemble(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index, const double pose[16], int64_t begin,
+             int64_t end, double* H, int nh, double* g, int ng, double* cost);
+int Solve(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* options, double* poses,
+          nlo_solve_result* results, double* trace, bool batched_call);
+}  // namespace multi
+
+}  // namespace nlo
+
+#endif  // NLO_HOST_H_

@@ -21,6 +21,13 @@ constexpr int kAcc3 = 10;             // 6 H + 3 g + cost
 constexpr int kMaxRanks = 8;
 constexpr int kSyncStride = 8 + 64;    // 8-byte words per registration of IterParams::sync_words
 constexpr int kPeerWords = 64;        // 8-byte words per (parity, source rank) slot of the peer exchange
+constexpr int kDebugIterations = 64;  // rows of IterParams::debug_times
+// Spin-wait limits (a wait that expires ends the solve with status 2 / NLO_ETIMEOUT or NLO_ECOMM, never a
+// hang).  The leader CTA may legitimately sit in the peer exchange for as long as another rank needs to
+// reach its own Solve (ingest skew, lazy module load, a time-sliced GPU), and the other CTAs of the grid
+// wait for the leader meanwhile, so the intra-grid limit has to be the longer one.
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ULL;  // 20 s
+constexpr unsigned long long kGridTimeoutNs = 60000000000ULL;  // 60 s
 
 // Per-registration optimisation state, resident in HBM for the whole solve.
 //   6-DoF / reprojection: t[3], q[4] (x,y,z,w), R = row-major rotation of q.
@@ -107,23 +114,17 @@ cudaError_t LaunchFinishStates(const State* states, double* poses16, double* res
 cudaError_t LaunchPackNdt(const double* point, const double* mean, const double* sqrt_info,
                           int64_t n, double* const planes[kNdtPlanes], int64_t dst_offset,
                           bool f32, cudaStream_t stream);
-cudaError_t LaunchPackNdtFromFloat(const float* point, const float* mean, const float* sqrt_info,
-                                   int64_t n, double* const planes[kNdtPlanes], cudaStream_t stream);
-cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
-                                 int64_t n_total, const int64_t* src_prefix,
-                                 const Range* ranges, int num_problems,
-                                 double* const planes[kNdtPlanes], cudaStream_t stream);
+// float input (fp32 storage mode only: f32 must be true)
+cudaError_t LaunchPackNdt(const float* point, const float* mean, const float* sqrt_info, int64_t n,
+                          double* const planes[kNdtPlanes], int64_t dst_offset, bool f32, cudaStream_t stream);
 cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t stride,
                              size_t off_point, size_t off_mean, size_t off_sqrt, int col_major,
-                             double* const planes[kNdtPlanes], cudaStream_t stream);
+                             double* const planes[kNdtPlanes], int64_t dst_offset, cudaStream_t stream);
 cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int64_t end,
                             double* point, double* mean, double* sqrt_info, bool f32,
                             cudaStream_t stream);
 cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
-                             double* const planes[kReprojPlanes], cudaStream_t stream);
-cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pixel, int64_t n_total,
-                                    const int64_t* src_prefix, const Range* ranges, int num_problems,
-                                    double* const planes[kReprojPlanes], cudaStream_t stream);
+                             double* const planes[kReprojPlanes], int64_t dst_offset, cudaStream_t stream);
 
 struct GenerateParams {
   double* planes[kNdtPlanes];
@@ -166,6 +167,9 @@ struct MatchParams {
   long long hash_mask;             // slots - 1 (slots is a power of two)
 };
 cudaError_t LaunchMatchNdt(const MatchParams& p, cudaStream_t stream);
+// Zeroes the last (matched mod 4) real hits in point-major order (the planar minimizer's truncation).
+cudaError_t LaunchTruncateNdt3Hits(double* const planes[kNdtPlanes], int64_t n, int max_neighbors,
+                                   const unsigned long long* matched, cudaStream_t stream);
 cudaError_t LaunchPackScan(const double* xyz, int64_t n, double* const planes[3], cudaStream_t stream);
 
 // Voxel hash of the sparse map: the reference keeps its NDT map in a std::unordered_map keyed by

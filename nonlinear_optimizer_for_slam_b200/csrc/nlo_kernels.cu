@@ -175,7 +175,7 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
           (parity * kMaxRanks + r) * kPeerWords + tid;
       unsigned long long w = *src;
       while (static_cast<unsigned int>(w >> 32) != seq32) {
-        if (GlobalTimerNs() - start > 5000000000ULL) {  // 5 s: a peer died; fail instead of hanging
+        if (GlobalTimerNs() - start > kPeerTimeoutNs) {  // a peer died; fail instead of hanging
           *pc.error = 1;
           break;
         }
@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   // profiling aid (NLO_DEBUG_TIMES=1): CTA 0 / thread 0 stamps the phases of each iteration
 #define NLO_STAMP(slot)                                                                  \
   do {                                                                                   \
-    if (p.debug_times != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)      \
+    if (p.debug_times != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 &&    \
+        it < kDebugIterations)                                                           \
       p.debug_times[static_cast<size_t>(it) * 8 + (slot)] = GlobalTimerNs();             \
   } while (0)
 
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           if (blockIdx.x == 0) {
             if (tid == 0) {
               while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
-                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
+                if (GlobalTimerNs() - start > kGridTimeoutNs) { sm.flag = 0; break; }
               __threadfence();
             }
             __syncthreads();
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
               const volatile unsigned long long* src = ll_state + tid;
               unsigned long long w = *src;
               while (static_cast<unsigned int>(w >> 32) != want) {
-                if (GlobalTimerNs() - start > 2000000000ULL) { sm.flag = 0; break; }
+                if (GlobalTimerNs() - start > kGridTimeoutNs) { sm.flag = 0; break; }
                 w = *src;
               }
               sm.halves[tid] = static_cast<unsigned int>(w);
@@ -735,63 +736,42 @@ __global__ void pack_ndt_kernel(const double* __restrict__ point, const double* 
 }
 
 __global__ void pack_ndt_from_float_kernel(const float* __restrict__ point, const float* __restrict__ mean,
-                                           const float* __restrict__ sqrt_info, int64_t n, PlanePtrs planes) {
+                                           const float* __restrict__ sqrt_info, int64_t n, PlanePtrs planes,
+                                           int64_t dst_offset) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t d = dst_offset + i;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], k, i) = point[3 * i + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], k, d) = point[3 * i + k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], 3 + k, i) = mean[3 * i + k];
+    for (int k = 0; k < 3; ++k) *NdtElem<float>(planes.p[0], 3 + k, d) = mean[3 * i + k];
     double S[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) S[k] = static_cast<double>(sqrt_info[9 * i + k]);
-    StoreNdtInformation<float>(planes.p[0], i, S);
-  }
-}
-
-// one CTA row per registration: source is the plain concatenation, destination is tile-aligned
-__global__ void pack_ndt_batched_kernel(const double* __restrict__ point,
-                                        const double* __restrict__ mean,
-                                        const double* __restrict__ sqrt_info,
-                                        const int64_t* __restrict__ src_prefix,
-                                        const Range* __restrict__ ranges, PlanePtrs planes) {
-  const int b = blockIdx.y;
-  const int64_t src0 = src_prefix[b];
-  const int64_t n = src_prefix[b + 1] - src0;
-  const int64_t dst0 = ranges[b].begin;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t s = src0 + i, d = dst0 + i;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], k, d) = point[3 * s + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], 3 + k, d) = mean[3 * s + k];
-    double S[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) S[k] = sqrt_info[9 * s + k];
-    StoreNdtInformation<double>(planes.p[0], d, S);
+    StoreNdtInformation<float>(planes.p[0], d, S);
   }
 }
 
 __global__ void pack_ndt_aos_kernel(const unsigned char* __restrict__ records, int64_t n,
                                     size_t stride_bytes, size_t off_point, size_t off_mean,
-                                    size_t off_sqrt, int col_major, PlanePtrs planes) {
+                                    size_t off_sqrt, int col_major, PlanePtrs planes, int64_t dst_offset) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const unsigned char* rec = records + static_cast<size_t>(i) * stride_bytes;
     const double* pt = reinterpret_cast<const double*>(rec + off_point);
     const double* mu = reinterpret_cast<const double*>(rec + off_mean);
     const double* S = reinterpret_cast<const double*>(rec + off_sqrt);
+    const int64_t d = dst_offset + i;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], k, i) = pt[k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], k, d) = pt[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], 3 + k, i) = mu[k];
+    for (int k = 0; k < 3; ++k) *NdtElem<double>(planes.p[0], 3 + k, d) = mu[k];
     double Srow[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int c = 0; c < 3; ++c) Srow[3 * r + c] = col_major ? S[3 * c + r] : S[3 * r + c];
-    StoreNdtInformation<double>(planes.p[0], i, Srow);
+    StoreNdtInformation<double>(planes.p[0], d, Srow);
   }
 }
 
@@ -810,34 +790,16 @@ __global__ void unpack_ndt_kernel(PlanePtrs planes, int64_t begin, int64_t end, 
 }
 
 __global__ void pack_reproj_kernel(const double* __restrict__ local_point,
-                                   const double* __restrict__ pixel, int64_t n, PlanePtrs planes) {
+                                   const double* __restrict__ pixel, int64_t n, PlanePtrs planes,
+                                   int64_t dst_offset) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t d = TiledOffset(kReprojPlanes, i);
+    const int64_t d = TiledOffset(kReprojPlanes, dst_offset + i);
     planes.p[0][d] = local_point[3 * i];
     planes.p[1][d] = local_point[3 * i + 1];
     planes.p[2][d] = local_point[3 * i + 2];
     planes.p[3][d] = pixel[2 * i];
     planes.p[4][d] = pixel[2 * i + 1];
-  }
-}
-
-__global__ void pack_reproj_batched_kernel(const double* __restrict__ local_point,
-                                           const double* __restrict__ pixel,
-                                           const int64_t* __restrict__ src_prefix,
-                                           const Range* __restrict__ ranges, PlanePtrs planes) {
-  const int b = blockIdx.y;
-  const int64_t src0 = src_prefix[b];
-  const int64_t n = src_prefix[b + 1] - src0;
-  const int64_t dst0 = ranges[b].begin;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t s = src0 + i, d = TiledOffset(kReprojPlanes, dst0 + i);
-    planes.p[0][d] = local_point[3 * s];
-    planes.p[1][d] = local_point[3 * s + 1];
-    planes.p[2][d] = local_point[3 * s + 2];
-    planes.p[3][d] = pixel[2 * s];
-    planes.p[4][d] = pixel[2 * s + 1];
   }
 }
 
@@ -867,35 +829,21 @@ cudaError_t LaunchPackNdt(const double* point, const double* mean, const double*
   return cudaGetLastError();
 }
 
-cudaError_t LaunchPackNdtFromFloat(const float* point, const float* mean, const float* sqrt_info,
-                                   int64_t n, double* const planes[kNdtPlanes], cudaStream_t stream) {
+cudaError_t LaunchPackNdt(const float* point, const float* mean, const float* sqrt_info, int64_t n,
+                          double* const planes[kNdtPlanes], int64_t dst_offset, bool f32, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
+  if (!f32) return cudaErrorInvalidValue;  // float input exists for the fp32 storage mode only
   pack_ndt_from_float_kernel<<<GridFor(n, 256), 256, 0, stream>>>(point, mean, sqrt_info, n,
-                                                                  MakePlanes(planes, kNdtPlanes));
-  return cudaGetLastError();
-}
-
-cudaError_t LaunchPackNdtBatched(const double* point, const double* mean, const double* sqrt_info,
-                                 int64_t n_total, const int64_t* src_prefix, const Range* ranges,
-                                 int num_problems, double* const planes[kNdtPlanes],
-                                 cudaStream_t stream) {
-  if (n_total <= 0) return cudaSuccess;
-  const int64_t per = (n_total + num_problems - 1) / num_problems;
-  int gx = static_cast<int>((per + 255) / 256);
-  if (gx > 64) gx = 64;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, num_problems);
-  pack_ndt_batched_kernel<<<grid, 256, 0, stream>>>(point, mean, sqrt_info, src_prefix, ranges,
-                                                    MakePlanes(planes, kNdtPlanes));
+                                                                  MakePlanes(planes, kNdtPlanes), dst_offset);
   return cudaGetLastError();
 }
 
 cudaError_t LaunchPackNdtAos(const unsigned char* records, int64_t n, size_t stride,
                              size_t off_point, size_t off_mean, size_t off_sqrt, int col_major,
-                             double* const planes[kNdtPlanes], cudaStream_t stream) {
+                             double* const planes[kNdtPlanes], int64_t dst_offset, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   pack_ndt_aos_kernel<<<GridFor(n, 256), 256, 0, stream>>>(
-      records, n, stride, off_point, off_mean, off_sqrt, col_major, MakePlanes(planes, kNdtPlanes));
+      records, n, stride, off_point, off_mean, off_sqrt, col_major, MakePlanes(planes, kNdtPlanes), dst_offset);
   return cudaGetLastError();
 }
 
@@ -913,24 +861,10 @@ cudaError_t LaunchUnpackNdt(double* const planes[kNdtPlanes], int64_t begin, int
 }
 
 cudaError_t LaunchPackReproj(const double* local_point, const double* pixel, int64_t n,
-                             double* const planes[kReprojPlanes], cudaStream_t stream) {
+                             double* const planes[kReprojPlanes], int64_t dst_offset, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   pack_reproj_kernel<<<GridFor(n, 256), 256, 0, stream>>>(local_point, pixel, n,
-                                                          MakePlanes(planes, kReprojPlanes));
-  return cudaGetLastError();
-}
-
-cudaError_t LaunchPackReprojBatched(const double* local_point, const double* pixel, int64_t n_total,
-                                    const int64_t* src_prefix, const Range* ranges, int num_problems,
-                                    double* const planes[kReprojPlanes], cudaStream_t stream) {
-  if (n_total <= 0) return cudaSuccess;
-  const int64_t per = (n_total + num_problems - 1) / num_problems;
-  int gx = static_cast<int>((per + 255) / 256);
-  if (gx > 64) gx = 64;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, num_problems);
-  pack_reproj_batched_kernel<<<grid, 256, 0, stream>>>(local_point, pixel, src_prefix, ranges,
-                                                       MakePlanes(planes, kReprojPlanes));
+                                                          MakePlanes(planes, kReprojPlanes), dst_offset);
   return cudaGetLastError();
 }
 
@@ -1159,6 +1093,36 @@ __global__ void match_ndt_kernel(const MatchParams m) {
 cudaError_t LaunchMatchNdt(const MatchParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   match_ndt_kernel<<<GridFor(p.n, 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// The planar minimizer of the reference processes floor(M / 4) * 4 of the M correspondences it is
+// given (..._analytic_3dof.cc:33-36); MatchPointCloud emits them point-major (point 0's hits, nearest
+// first, then point 1's, ...; tests/simple_optimization_test.cc:318-340).  The device matcher keeps a
+// fixed slot layout (slot j of point i at j * n + i, empty slots with zero information), so the
+// M mod 4 hits the reference would drop are the LAST real hits in point-major order: walk back from
+// (n - 1, last slot) and zero their information (exact zero contribution).  One thread: it stops
+// after at most 3 hits.
+__global__ void truncate_ndt3_hits_kernel(PlanePtrs planes, int64_t n, int max_neighbors,
+                                          const unsigned long long* matched) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int drop = static_cast<int>(*matched % 4ULL);
+  for (int64_t i = n - 1; i >= 0 && drop > 0; --i)
+    for (int j = max_neighbors - 1; j >= 0 && drop > 0; --j) {
+      const int64_t o = static_cast<int64_t>(j) * n + i;
+      // a real hit carries a valid cell's information matrix, whose trace is positive
+      const double trace = *NdtElem<double>(planes.p[0], 6, o) + *NdtElem<double>(planes.p[0], 9, o) +
+                           *NdtElem<double>(planes.p[0], 11, o);
+      if (trace > 0.0) {
+        for (int k = 0; k < 6; ++k) *NdtElem<double>(planes.p[0], 6 + k, o) = 0.0;
+        --drop;
+      }
+    }
+}
+cudaError_t LaunchTruncateNdt3Hits(double* const planes[kNdtPlanes], int64_t n, int max_neighbors,
+                                   const unsigned long long* matched, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  truncate_ndt3_hits_kernel<<<1, 32, 0, stream>>>(MakePlanes(planes, kNdtPlanes), n, max_neighbors, matched);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "nlo_cuda.h"
 #include "nonlinear_optimizer/loss_function.h"
@@ -17,11 +18,15 @@
 namespace nonlinear_optimizer {
 namespace cuda_backend {
 
-// One context (device + stream) per minimizer instance, like the reference's minimizers hold their
-// own scratch.  Minimizers are not re-entrant per instance (same contract as the reference).
+// One context per minimizer instance, like the reference's minimizers hold their own scratch: one
+// device + stream, or -- given a device list -- several B200s of this process, over which Solve splits
+// the correspondence vector by point range exactly where the reference splits it over its thread pool
+// (..._analytic.cc:59-73,104-119).  Minimizers are not re-entrant per instance (same contract as the
+// reference).
 class Session {
  public:
-  explicit Session(int device = 0) : device_(device) {}
+  explicit Session(int device = 0) : devices_(1, device) {}
+  explicit Session(const std::vector<int>& devices) : devices_(devices) {}
   ~Session() {
     if (problem_ != nullptr) nlo_problem_destroy(ctx_, problem_);
     if (ctx_ != nullptr) nlo_context_destroy(ctx_);
@@ -31,9 +36,16 @@ class Session {
 
   bool EnsureContext() {
     if (ctx_ != nullptr) return true;
-    const int rc = nlo_context_create(device_, &ctx_);
+    int rc = NLO_EINVAL;
+    if (devices_.size() == 1) {
+      rc = nlo_context_create(devices_[0], &ctx_);
+    } else if (!devices_.empty()) {
+      std::vector<int32_t> dev(devices_.begin(), devices_.end());
+      rc = nlo_context_create_multi(dev.data(), static_cast<int32_t>(dev.size()), &ctx_);
+    }
     if (rc != NLO_OK) {
-      std::cerr << "nlo_context_create(device " << device_ << ") failed with " << rc
+      std::cerr << "nlo_context_create (" << devices_.size() << " device(s), first "
+                << (devices_.empty() ? -1 : devices_[0]) << ") failed with " << rc
                 << ": no usable sm_100 GPU (there is no CPU fallback)" << std::endl;
       ctx_ = nullptr;
       return false;
@@ -88,7 +100,7 @@ class Session {
   nlo_problem* problem() { return problem_; }
 
  private:
-  int device_;
+  std::vector<int> devices_;
   nlo_context* ctx_{nullptr};
   nlo_problem* problem_{nullptr};
   int64_t capacity_{0};

@@ -12,6 +12,11 @@
 //     or when the loss cannot be expressed on the device; the reference always returns true.
 //   * the executor is ignored, so the `N mod num_threads` tail the reference's threaded path drops
 //     is processed (result = the reference's single-thread result).
+//   * constructed with a device LIST, Solve splits the correspondences by point range over those
+//     B200s (one process, peer-mapped exchange buffers, one all-reduce of the 28 / 10 sums per
+//     iteration inside the iteration kernel) -- the place where the reference splits them over its
+//     thread pool (..._analytic.cc:59-73,104-119).  The pose is bit-identical to the 1-GPU one only up
+//     to the summation order of the shards (1e-12 relative on H, g).
 #ifndef NONLINEAR_OPTIMIZER_MAHALANOBIS_DISTANCE_MINIMIZER_MAHALANOBIS_DISTANCE_MINIMIZER_CUDA_H_
 #define NONLINEAR_OPTIMIZER_MAHALANOBIS_DISTANCE_MINIMIZER_MAHALANOBIS_DISTANCE_MINIMIZER_CUDA_H_
 
@@ -47,6 +52,7 @@ inline bool UploadCorrespondences(cuda_backend::Session* session,
 class MahalanobisDistanceMinimizerCuda : public MahalanobisDistanceMinimizer {
  public:
   explicit MahalanobisDistanceMinimizerCuda(int device = 0) : session_(device) {}
+  explicit MahalanobisDistanceMinimizerCuda(const std::vector<int>& devices) : session_(devices) {}
 
   bool Solve(const Options& options, const std::vector<Correspondence>& correspondences,
              Pose* pose) final {
@@ -54,15 +60,18 @@ class MahalanobisDistanceMinimizerCuda : public MahalanobisDistanceMinimizer {
     if (!session_.ApplyLoss(loss_function_)) return false;
     if (!internal::UploadCorrespondences(&session_, correspondences)) return false;
     const nlo_solve_options o = cuda_backend::Session::ToC(options);
-    nlo_solve_result result;
+    nlo_solve_result result{};
     const int rc = nlo_ndt6_solve(session_.ctx(), session_.problem(), &o, PoseData(*pose), &result,
                                   nullptr);
-    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
     last_result_ = result;
-    return rc == NLO_OK ? true : session_.Report("nlo_ndt6_solve", rc);
+    if (rc != NLO_OK) return session_.Report("nlo_ndt6_solve", rc);
+    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
+    return true;
   }
 
   const nlo_solve_result& last_result() const { return last_result_; }
+  // wall / host-gather milliseconds of the last Solve's ingest (nlo_ingest_stats)
+  void last_ingest_ms(double* total_ms, double* host_gather_ms) { nlo_ingest_stats(session_.ctx(), total_ms, host_gather_ms); }
 
  private:
   cuda_backend::Session session_;
@@ -72,6 +81,7 @@ class MahalanobisDistanceMinimizerCuda : public MahalanobisDistanceMinimizer {
 class MahalanobisDistanceMinimizerCuda3DOF : public MahalanobisDistanceMinimizer {
  public:
   explicit MahalanobisDistanceMinimizerCuda3DOF(int device = 0) : session_(device) {}
+  explicit MahalanobisDistanceMinimizerCuda3DOF(const std::vector<int>& devices) : session_(devices) {}
 
   bool Solve(const Options& options, const std::vector<Correspondence>& correspondences,
              Pose* pose) final {
@@ -79,15 +89,18 @@ class MahalanobisDistanceMinimizerCuda3DOF : public MahalanobisDistanceMinimizer
     if (!session_.ApplyLoss(loss_function_)) return false;
     if (!internal::UploadCorrespondences(&session_, correspondences)) return false;
     const nlo_solve_options o = cuda_backend::Session::ToC(options);
-    nlo_solve_result result;
+    nlo_solve_result result{};
     const int rc = nlo_ndt3_solve(session_.ctx(), session_.problem(), &o, PoseData(*pose), &result,
                                   nullptr);
-    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
     last_result_ = result;
-    return rc == NLO_OK ? true : session_.Report("nlo_ndt3_solve", rc);
+    if (rc != NLO_OK) return session_.Report("nlo_ndt3_solve", rc);
+    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
+    return true;
   }
 
   const nlo_solve_result& last_result() const { return last_result_; }
+  // wall / host-gather milliseconds of the last Solve's ingest (nlo_ingest_stats)
+  void last_ingest_ms(double* total_ms, double* host_gather_ms) { nlo_ingest_stats(session_.ctx(), total_ms, host_gather_ms); }
 
  private:
   cuda_backend::Session session_;

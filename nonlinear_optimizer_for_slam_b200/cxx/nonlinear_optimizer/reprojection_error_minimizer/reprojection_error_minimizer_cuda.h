@@ -5,6 +5,7 @@
 #ifndef NONLINEAR_OPTIMIZER_REPROJECTION_ERROR_MINIMIZER_REPROJECTION_ERROR_MINIMIZER_CUDA_H_
 #define NONLINEAR_OPTIMIZER_REPROJECTION_ERROR_MINIMIZER_REPROJECTION_ERROR_MINIMIZER_CUDA_H_
 
+#include <cstddef>
 #include <iostream>
 #include <vector>
 
@@ -17,6 +18,7 @@ namespace reprojection_error_minimizer {
 class ReprojectionErrorMinimizerCuda : public ReprojectionErrorMinimizer {
  public:
   explicit ReprojectionErrorMinimizerCuda(int device = 0) : session_(device) {}
+  explicit ReprojectionErrorMinimizerCuda(const std::vector<int>& devices) : session_(devices) {}
 
   bool Solve(const Options& options, const std::vector<Correspondence>& correspondences,
              const CameraIntrinsics& camera_intrinsics, Pose* pose) final {
@@ -24,29 +26,26 @@ class ReprojectionErrorMinimizerCuda : public ReprojectionErrorMinimizer {
     if (!session_.ApplyLoss(loss_function_)) return false;
     const int64_t n = static_cast<int64_t>(correspondences.size());
     if (!session_.EnsureProblem(n, /*reproj=*/true)) return false;
-    // 40-byte records: split into the two host arrays of the C ABI (the only host-side repack;
-    // 5 doubles per correspondence)
-    points_.resize(3 * correspondences.size());
-    pixels_.resize(2 * correspondences.size());
-    FlattenCorrespondences(correspondences.data(), correspondences.size(), points_.data(),
-                           pixels_.data());
+    // the reference's 40-byte records are ingested in place (no host-side repack)
     const double K[6] = {camera_intrinsics.fx, camera_intrinsics.fy, camera_intrinsics.cx,
                          camera_intrinsics.cy, camera_intrinsics.inv_fx, camera_intrinsics.inv_fy};
-    int rc = nlo_reproj_upload(session_.ctx(), session_.problem(), n, points_.data(), pixels_.data(), K);
-    if (rc != NLO_OK) return session_.Report("nlo_reproj_upload", rc);
+    int rc = nlo_reproj_upload_aos(session_.ctx(), session_.problem(), n, correspondences.data(),
+                                   sizeof(Correspondence), offsetof(Correspondence, local_point),
+                                   offsetof(Correspondence, matched_pixel), K);
+    if (rc != NLO_OK) return session_.Report("nlo_reproj_upload_aos", rc);
     const nlo_solve_options o = cuda_backend::Session::ToC(options);
-    nlo_solve_result result;
+    nlo_solve_result result{};
     rc = nlo_reproj_solve(session_.ctx(), session_.problem(), &o, PoseData(*pose), &result, nullptr);
-    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
     last_result_ = result;
-    return rc == NLO_OK ? true : session_.Report("nlo_reproj_solve", rc);
+    if (rc != NLO_OK) return session_.Report("nlo_reproj_solve", rc);
+    std::cerr << "COST: " << result.final_cost << ", iter: " << result.iterations << std::endl;
+    return true;
   }
 
   const nlo_solve_result& last_result() const { return last_result_; }
 
  private:
   cuda_backend::Session session_;
-  std::vector<double> points_, pixels_;
   nlo_solve_result last_result_{};
 };
 

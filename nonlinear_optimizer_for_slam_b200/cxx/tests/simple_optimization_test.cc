@@ -5,6 +5,7 @@
 //   mahalanobis_distance_minimizer/tests/3dof_6dof_comparison_test.cc (planar variant)
 // of /root/reference/nonlinear_optimizer.  The reference prints poses for a human to compare with
 // "True pose"; here each case checks the numbers.  Needs a B200; exits non-zero on any failure.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -355,6 +356,75 @@ void TestDeviceRegistration(bool planar) {
   for (int k = 0; k < 16; ++k) CHECK_NEAR(PoseData(hashed_pose)[k], PoseData(pose)[k], 1e-8);
 }
 
+// Solve() over several B200s of this process (a device list) against the same Solve() on one:
+// the split by point range sits inside Solve, where the reference splits over its thread pool
+// (..._analytic.cc:59-73,104-119).  On a one-GPU box the list names device 0 twice: two shards, two
+// iteration kernels and the same peer-memory all-reduce between them, on one device.
+void TestShardedSolve(bool planar) {
+  using namespace mahalanobis_distance_minimizer;
+  const int visible = nlo_visible_device_count();
+  CHECK_TRUE(visible >= 1);
+  std::vector<int> devices;
+  const int D = visible >= 2 ? std::min(visible, 8) : 2;
+  for (int r = 0; r < D; ++r) devices.push_back(visible >= 2 ? r : 0);
+  const size_t n = visible >= 2 ? 4000003 : 600001;  // not a multiple of 4 * D: the planar tail rule is global
+  const Pose true_pose = planar ? YawPose(-0.15, 0.05, 0.0, 0.2) : YawPose(-0.2, 0.123, 0.3, 0.1);
+  const Pose true_inv = Inverse(true_pose);
+  std::vector<Correspondence> correspondences(n);
+  uint64_t state = 88172645463325252ull;
+  auto uniform = [&]() {
+    state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+    return static_cast<double>(state >> 11) * (1.0 / 9007199254740992.0);
+  };
+  for (size_t i = 0; i < n; ++i) {
+    // a point on the floor or on the y = -2.5 wall, its 0.5 m planar cell, 1 cm noise across the surface
+    const bool floor_hit = uniform() < 0.6;
+    double w[3] = {-3.5 + 7.0 * uniform(), floor_hit ? -2.5 + 5.0 * uniform() : -2.5,
+                   floor_hit ? 0.0 : 2.5 * uniform()};
+    const int normal = floor_hit ? 2 : 1;
+    Correspondence& c = correspondences[i];
+    for (int k = 0; k < 3; ++k) c.ndt.mean(k) = (k == normal) ? w[k] : (std::floor(w[k] * 2.0) + 0.5) * 0.5;
+    w[normal] += 0.02 * (uniform() - 0.5);
+    double l[3];
+    Apply(true_inv, w, l);
+    for (int k = 0; k < 3; ++k) c.point(k) = l[k];
+    c.ndt.is_valid = true;
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col)
+        c.ndt.sqrt_information(r, col) = (r == col) ? (r == normal ? 69.3 : 6.93) : 0.0;
+    // an off-diagonal term so that the column-major ingest matters
+    c.ndt.sqrt_information(0, 1) = 0.37;
+  }
+  Options options;
+  auto solve = [&](std::unique_ptr<MahalanobisDistanceMinimizer> optimizer, Pose* pose, nlo_solve_result* res) {
+    optimizer->SetLossFunction(std::make_shared<ExponentialLossFunction>(1.0, 1.0));
+    *pose = Pose::Identity();
+    CHECK_TRUE(optimizer->Solve(options, correspondences, pose));
+    *res = planar ? static_cast<MahalanobisDistanceMinimizerCuda3DOF*>(optimizer.get())->last_result()
+                  : static_cast<MahalanobisDistanceMinimizerCuda*>(optimizer.get())->last_result();
+  };
+  Pose one, many;
+  nlo_solve_result res_one{}, res_many{};
+  if (planar) {
+    solve(std::make_unique<MahalanobisDistanceMinimizerCuda3DOF>(0), &one, &res_one);
+    solve(std::make_unique<MahalanobisDistanceMinimizerCuda3DOF>(devices), &many, &res_many);
+  } else {
+    solve(std::make_unique<MahalanobisDistanceMinimizerCuda>(0), &one, &res_one);
+    solve(std::make_unique<MahalanobisDistanceMinimizerCuda>(devices), &many, &res_many);
+  }
+  std::cerr << "sharded Solve over " << D << " device(s) (" << visible << " visible), " << n
+            << " correspondences: iterations " << res_one.iterations << " / " << res_many.iterations
+            << ", cost " << res_one.final_cost << " / " << res_many.final_cost << std::endl;
+  CHECK_TRUE(res_one.iterations == res_many.iterations);
+  CHECK_TRUE(res_one.iterations >= 2);
+  CHECK_NEAR(res_many.final_cost, res_one.final_cost, 1e-9 * std::fabs(res_one.final_cost));
+  // the shards change only the order of the fp64 sums (every device of the sharded solve itself
+  // ends bit-identical: nlo_ndt*_solve fails with NLO_ECOMM otherwise)
+  for (int k = 0; k < 16; ++k) CHECK_NEAR(PoseData(many)[k], PoseData(one)[k], 1e-9);
+  CHECK_NEAR(PoseData(one)[12], PoseData(true_pose)[12], 5e-3);
+  CHECK_NEAR(PoseData(one)[13], PoseData(true_pose)[13], 5e-3);
+}
+
 }  // namespace
 
 int main(int, char**) {
@@ -367,6 +437,9 @@ int main(int, char**) {
   std::cerr << "Start NdtRegistrationCuda" << std::endl;
   TestDeviceRegistration(false);
   TestDeviceRegistration(true);
+  std::cerr << "Start sharded Solve (device list)" << std::endl;
+  TestShardedSolve(false);
+  TestShardedSolve(true);
   if (g_failures == 0) std::cerr << "ALL CXX TESTS PASSED" << std::endl;
   return g_failures == 0 ? 0 : 1;
 }

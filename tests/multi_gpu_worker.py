@@ -41,11 +41,12 @@ def main():
         point, mean, S = syn.ndt_problem(n, seed, true_T)
         total = len(point)
         if kind == "ndt3":
-            total = (total // (4 * world)) * 4 * world  # keep every shard a multiple of 4 (floor(n/4)*4 rule)
+            total -= (total % 4 + 1) % 4                # n mod 4 == 3: the dropped tail spans ranks' ends
             point, mean, S = point[:total], mean[:total], S[:total]
         b, e = sharding.point_range(total, rank, world)
         prob = nlo.NdtProblem(ctx, capacity=e - b)
         prob.upload(point[b:e], mean[b:e], S[b:e])
+        prob.set_global_range(b, total)                 # the planar tail rule is global
         ctx.set_loss(*loss)
         pose0 = nlo.identity_pose()
         if kind == "ndt6":
@@ -55,12 +56,21 @@ def main():
             Hr, gr, cr = oracle.ndt6_assemble(point, mean, S, np.eye(3), np.zeros(3), *loss, long_double=True)
             nh, ng = 21, 6
         else:
-            H, g, c = prob.assemble3(pose0)
+            end_local = max(0, min(e - b, (total // 4) * 4 - b))
+            H, g, c = prob.assemble3(pose0, 0, end_local)
             res = prob.solve3(pose0, trace=True)
             ref = oracle.ndt3_solve(point, mean, S, pose0, *loss)
             Hr, gr, cr = oracle.ndt3_assemble(point, mean, S, np.eye(2), np.zeros(2), *loss, long_double=True)
             nh, ng = 6, 3
         assert_sums_close(H, g, c, Hr, gr, cr)
+        # the same sums from the ranks' own, un-reduced parts (communicator suspended), added in rank order
+        ctx.comm_suspend(True)
+        Hl, gl, cl = prob.assemble6(pose0) if kind == "ndt6" else prob.assemble3(pose0, 0, end_local)
+        ctx.comm_suspend(False)
+        parts = [None] * world
+        dist.all_gather_object(parts, np.concatenate([Hl, gl, [cl]]))
+        tot = sharding.ordered_sum(parts)
+        assert_sums_close(H, g, c, tot[:nh], tot[nh:nh + ng], tot[nh + ng], tol=1e-12)
         pose_r, it_r, cost_r, trace_r = ref
         assert res["iterations"] == it_r, (res["iterations"], it_r)
         for k in range(trace_r.shape[0]):

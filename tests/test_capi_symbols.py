@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol(nlo):
         assert hasattr(lib, name), name
     # and the ctypes binding covers exactly the declared set
     assert sorted(nlo._capi.declared_symbols()) == declared
-    assert nlo._capi.load().nlo_abi_version() == 1
+    assert nlo._capi.load().nlo_abi_version() == 2
 
 
 def test_only_the_abi_is_exported():

@@ -91,9 +91,47 @@ def test_register_matches_oracle_outer_loop(ctx, nlo, oracle):
     assert np.max(np.abs(ta - tb)) < 1e-6 and rotation_angle(Ra, Rb) < 1e-6
     # and it actually registers the scan (the reference's own runs end a few mm from the truth)
     np.testing.assert_allclose(tb, syn.CFG1_TRUE[:3, 3], atol=1e-2)
-    # planar variant runs through the same loop
-    res3 = scan.register(ndt_map, nlo.identity_pose(), three_dof=True)
-    assert res3["outer_iterations"] >= 1
+    scan.close(); ndt_map.close()
+
+
+@pytest.mark.parametrize("n_points", [20001, 20002, 20003])
+def test_register_3dof_matches_oracle_outer_loop(ctx, nlo, oracle, n_points):
+    """The planar registration loop of 3dof_6dof_comparison_test.cc: the reference hands the planar
+    minimizer MatchPointCloud's POINT-MAJOR list of real hits and the minimizer drops the last
+    M mod 4 of them (..._analytic_3dof.cc:33-36).  The device loop must drop exactly those: same
+    rounds, same inner iterations, same pose as the host loop with the numpy matcher + oracle."""
+    grid = syn.room_ndt_grid(1.0)
+    rng = np.random.default_rng(n_points)
+    world = syn.room_surface_samples(n_points, rng, 0.01)
+    Tinv = np.linalg.inv(syn.CFG2_TRUE)
+    local = world @ Tinv[:3, :3].T + Tinv[:3, 3]
+    ctx.set_loss(1, [1.0, 1.0])
+    ndt_map = nlo.NdtMap(ctx, grid=grid)
+    scan = nlo.Scan(ctx, local)
+    res = scan.register(ndt_map, nlo.identity_pose(), three_dof=True)
+    pose = nlo.identity_pose()
+    outer_done, inner, remainders = 0, 0, set()
+    for outer in range(10):
+        R, t = nlo.pose_to_Rt(pose)
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+        ref = brute_force_match(local, T, grid)
+        has = ref >= 0                                   # [n, 2], point-major order when flattened
+        pidx = np.repeat(np.arange(len(local)), 2).reshape(-1, 2)[has]
+        cidx = ref[has]
+        remainders.add(len(pidx) % 4)
+        last = pose.copy()
+        pose, it, cost, _ = oracle.ndt3_solve(local[pidx], grid["mean"][cidx], grid["sqrt_info"][cidx], pose,
+                                              1, [1.0, 1.0])
+        outer_done += 1; inner += it
+        Ra, ta = nlo.pose_to_Rt(last); Rb, tb = nlo.pose_to_Rt(pose)
+        dq = oracle.rotmat_to_quat(Ra.T @ Rb)
+        if np.linalg.norm(Ra.T @ (tb - ta)) < 1e-5 and np.linalg.norm(dq[:3]) < 1e-5:
+            break
+    assert res["outer_iterations"] == outer_done
+    assert res["inner_iterations"] == inner
+    Ra, ta = nlo.pose_to_Rt(res["pose"]); Rb, tb = nlo.pose_to_Rt(pose)
+    assert np.max(np.abs(ta - tb)) < 1e-6 and rotation_angle(Ra, Rb) < 1e-6
+    assert res["pose"][14] == 0.0                        # z untouched (..._analytic_3dof.cc:104-105)
     scan.close(); ndt_map.close()
 
 
