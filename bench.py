@@ -214,21 +214,35 @@ def cpu_reference_rates(sample_points, min_seconds, threads):
     return n, out
 
 
+def workload_name(total):
+    return ("cfg4: NDT 6-DoF, %d-point scan vs 0.5 m-voxel NDT map, Exponential(1,1), sharded by point range"
+            % total)
+
+
 def run_reference(args):
+    """The reference's own CPU path on the SAME workload: one step = one float AVX2+FMA SoA assembly
+    pass (SolveFloatIntrinsicAligned restated, thread split of ..._analytic_simd.cc:55-76) over all
+    `--points` correspondences on every host thread.  The scan is the cfg4 generator's first 4M
+    correspondences tiled to the full size (the rate does not depend on the values; 64Mi points are
+    4 GB of float planes)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 4_000_000
-    # each "step" is one assembly pass over the bounded sample; W warm-up, K timed
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import nlo_oracle_py as oracle
     from nonlinear_optimizer_for_slam_b200 import synthetic as syn
     oracle.build()
     native = oracle.use_native_build()   # -march=native on this host, as the reference builds
-    point, mean, S = syn.ndt_problem(sample, SEED, syn.CFG1_TRUE)
-    n = len(point)
-    planes = oracle.simd_pack(point, mean, S)
+    total = args.points
+    block = min(total, 4 * 1024 * 1024)
+    point, mean, S = syn.ndt_problem(block + block // 64, SEED, syn.CFG1_TRUE)
+    assert len(point) >= block
+    point, mean, S = point[:block], mean[:block], S[:block]
+    base = oracle.simd_pack(point, mean, S).reshape(15, block)
+    reps = (total + block - 1) // block
+    planes = np.ascontiguousarray(np.tile(base, (1, reps))[:, :total]).reshape(-1)
+    n = total
     R = np.eye(3); t = np.zeros(3)
     step = lambda: oracle.simd_ndt6_assemble(planes, n, R, t, 1, [1.0, 1.0], threads)
     for _ in range(max(args.warmup, 1)):
@@ -238,21 +252,20 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = n * args.steps / dt / 1e9
-    # the double-precision scalar path, for the record
+    # the double-precision scalar path on one block, for the record
     ts = time.perf_counter()
     oracle.ndt6_assemble_threads(point, mean, S, R, t, 1, [1.0, 1.0], threads)
-    scalar = n / (time.perf_counter() - ts) / 1e9
-    sample_txt = ("%d correspondences of cfg4 (same generator, seed %d) per step, float AVX2+FMA SoA "
-                  "assembly (SolveFloatIntrinsicAligned restated) on %d std::threads, %s"
-                  % (n, SEED, threads, "-O2 -march=native" if native else "-O2 -mavx2 -mfma"))
+    scalar = block / (time.perf_counter() - ts) / 1e9
+    sample_txt = ("all %d correspondences of cfg4 per step (the generator's first %d, seed %d, tiled), float "
+                  "AVX2+FMA SoA assembly (SolveFloatIntrinsicAligned restated) on %d std::threads, %s"
+                  % (n, block, SEED, threads, "-O2 -march=native" if native else "-O2 -mavx2 -mfma"))
     line = {
         "impl": "reference", "metric": "NDT 6-DoF assembly Gpoints/s", "value": value,
         "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cfg4: NDT 6-DoF, 64M-point scan vs 0.5 m-voxel NDT map, Exponential(1,1)",
-                   "sample_points": n},
+        "config": {"workload": workload_name(total), "points_total": total},
         "cpu_baseline": {"value": value, "unit": "Gpoints/s", "cores": threads, "kind": "port",
                          "sample": sample_txt, "scalar_f64_gpoints_s": scalar},
         "e2e": {"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -347,6 +360,7 @@ def run_cuda(args):
         per_rank_ms = [None] * world
         dist.all_gather_object(per_rank_ms, ms_local)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    parity = parity_check(nlo, ctx, prob, res, n_local, rank, world, dist)
 
     value = total * args.steps / (ms * 1e-3) / 1e9
     iters_per_s = args.steps / (ms * 1e-3)
@@ -363,11 +377,27 @@ def run_cuda(args):
     if not args.no_extra:
         if world == 1:
             extra = measure_small_configs(nlo, syn, ctx)
+            if not args.no_cpu:
+                try:
+                    sec = cpu_secondary_rates(syn, os.cpu_count() or 1)
+                    extra["secondary"]["cfg2_ndt3_1m_huber"]["cpu_baseline"] = sec["cfg2"]
+                    extra["secondary"]["cfg3_pnp_50k_cauchy"]["cpu_baseline"] = sec["cfg3"]
+                except Exception as e:
+                    extra["secondary"]["cpu_baseline_error"] = str(e)
         if comm != "none":
             ctx.comm_destroy()   # cfg5 partitions independent registrations: no collective at all
             comm_destroyed = True
         extra.setdefault("secondary", {})["cfg5_batched_4096x20k"] = measure_batched(
             nlo, syn, ctx, rank, world, dist)
+
+    dropin = None
+    if not args.no_dropin:
+        if dist is not None:
+            ctx.synchronize(); dist.barrier()
+        if rank == 0:
+            dropin = measure_dropin(world)
+        if dist is not None:
+            dist.barrier()       # the other ranks' GPUs stay idle while rank 0's child process uses them
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -392,8 +422,7 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gn_iterations_per_s": iters_per_s,
             "per_rank_ms_per_step": [round(v / args.steps, 6) for v in per_rank_ms],
-            "config": {"workload": "cfg4: NDT 6-DoF, %d-point scan vs 0.5 m-voxel NDT map, "
-                                   "Exponential(1,1), sharded by point range" % total,
+            "config": {"workload": workload_name(total),
                        "points_total": total, "points_per_gpu": n_local, "comm": comm,
                        "bytes_per_correspondence": BYTES_PER_CORR,
                        "storage": "fp64, 12 scalars per correspondence: point 3 + mean 3 + S^T S (6 unique), "
@@ -403,12 +432,17 @@ def run_cuda(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(n_local, args.steps if comm != "nccl" else 1),
+                         "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read + dram__bytes_write of "
+                                           "one `ncu --set full` capture of this kernel at 64M points, scaled by "
+                                           "points x iterations of this launch (not measured in this run)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_iteration": n_local * BYTES_PER_CORR,
                          "algorithmic_bytes_per_launch": n_local * BYTES_PER_CORR * (args.steps if comm != "nccl" else 1),
                          "kernel": "gn_iteration_kernel<ndt6, exponential>"},
             "cpu_baseline": cpu,
+            "parity_check": parity,
             "e2e": e2e,
+            "e2e_dropin": dropin,
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -419,6 +453,56 @@ def run_cuda(args):
         barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def parity_check(nlo, ctx, prob, res, n_local, rank, world, dist):
+    """Correctness of THIS run, visible in the JSON line at every N:
+      * the all-reduced H | g | cost of the sharded assembly against the ranks' own un-reduced sums
+        (communicator suspended) gathered over gloo and added on the host in rank order;
+      * every rank's final pose of the timed solve, bit for bit;
+      * every rank's first (up to) 1M correspondences, read back from the device, against the
+        long-double CPU oracle.
+    The run fails above 1e-6 (BASELINE.json north_star tolerance)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import nlo_oracle_py as oracle
+    from parity import rel_errors
+    from nonlinear_optimizer_for_slam_b200 import sharding, synthetic as syn
+    T = syn.yaw_pose([0.05, -0.02, 0.03], 0.02)          # not the identity: R enters the sums
+    pose = syn.to_pose16(T)
+    H, g, c = prob.assemble6(pose)                       # all-reduced over the ranks
+    if world > 1:
+        ctx.comm_suspend(True)
+    Hl, gl, cl = prob.assemble6(pose)                    # this rank's shard only
+    m = min(n_local, 1 << 20)
+    Hs, gs, cs = prob.assemble6(pose, 0, m)
+    if world > 1:
+        ctx.comm_suspend(False)
+    p, mu, info = prob.download(0, m)
+    S = syn.sqrt_info_from_information6(info)
+    Rq = oracle.quat_to_rotmat(oracle.rotmat_to_quat(T[:3, :3]))
+    Ho, go, co = oracle.ndt6_assemble(p, mu, S, Rq, T[:3, 3], 1, [1.0, 1.0], long_double=True)
+    e_oracle = max(rel_errors(Hs, gs, cs, Ho, go, co))
+    local = np.concatenate([Hl, gl, [cl]])
+    parts, poses, e_or = [local], [res["pose"].tobytes()], [e_oracle]
+    if dist is not None:
+        parts = [None] * world; poses = [None] * world; e_or = [None] * world
+        dist.all_gather_object(parts, local)
+        dist.all_gather_object(poses, res["pose"].tobytes())
+        dist.all_gather_object(e_or, e_oracle)
+    tot = sharding.ordered_sum(parts)
+    eh, eg, ec = rel_errors(H, g, c, tot[:21], tot[21:27], tot[27])
+    out = {"err_H": eh, "err_g": eg, "err_cost": ec, "pose_identical": all(q == poses[0] for q in poses),
+           "n_ranks": world, "oracle_sample_points_per_rank": m, "err_vs_oracle_max_over_ranks": max(e_or),
+           "tolerance": 1e-6,
+           "what": "all-reduced sums vs rank-ordered host sum of the ranks' un-reduced sums; final pose of "
+                   "the timed solve bit-identical on all ranks; each rank's first correspondences vs the "
+                   "long-double CPU oracle"}
+    ok = eh < 1e-6 and eg < 1e-6 and ec < 1e-6 and out["pose_identical"] and max(e_or) < 1e-6
+    out["ok"] = bool(ok)
+    if not ok:
+        raise SystemExit("parity check failed: %s" % json.dumps(out))
+    return out
 
 
 def syn_module():
@@ -483,6 +567,82 @@ def measure_e2e(nlo, ctx, prob, n_local, args, dist, total):
             "note": "one step of the e2e arm = one GN iteration inside a full Solve(): pinned host "
                     "correspondences uploaded once per Solve (as the reference's Solve receives them), "
                     "%d iterations on the device, pose + iteration count read back" % iters}
+
+
+def measure_dropin(world):
+    """The reference-facing call itself, timed by the C++ binary cxx/bench/dropin_bench:
+    MahalanobisDistanceMinimizerCuda::Solve(options, std::vector<Correspondence> (304-byte AoS records,
+    pageable), &pose) in ONE process over `world` GPUs (device list; the split sits inside Solve)."""
+    from nonlinear_optimizer_for_slam_b200 import build as nlo_build
+    out = {}
+    try:
+        binary = nlo_build.build_cxx_bench()
+    except Exception as e:
+        return {"error": "dropin_bench did not build: %s" % e}
+    devices = ",".join(str(d) for d in range(world))
+    cases = (("cfg1_100k_converged", ["--n", "100000"]),
+             ("cfg1_100k_40_iterations", ["--n", "100000", "--force-iterations"]),
+             ("cfg4_16M_40_iterations", ["--n", str(16 * 1024 * 1024), "--force-iterations"]),
+             ("cfg2_1M_planar_huber_40_iterations", ["--n", "1000000", "--planar", "--loss", "huber",
+                                                     "--force-iterations"]))
+    for name, extra in cases:
+        try:
+            r = subprocess.run([binary, "--devices", devices] + extra, capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                out[name] = {"error": (r.stderr or "")[-400:]}
+                continue
+            out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            out[name] = {"error": str(e)}
+    out["note"] = ("timed region = ...Cuda::Solve() on the reference's AoS records in pageable memory: host gather of "
+                   "the 15 hot doubles into a pinned ring, PCIe, device repack, the device-resident loop, pose read-back; "
+                   "gpoints_s = n x assemblies / wall")
+    return out
+
+
+def cpu_secondary_rates(syn, threads):
+    """The reference's float SIMD twins of the planar and reprojection minimizers, timed beside cfg2 / cfg3
+    on this host: as the reference runs them (ONE thread: neither uses the executor) and with the 8-lane
+    thread split applied on all threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nlo_oracle_py as oracle
+    oracle.build()
+    native = oracle.use_native_build()
+    flags = "-O2 -march=native" if native else "-O2 -mavx2 -mfma"
+
+    def rate(fn, n, min_seconds=1.5):
+        fn()
+        passes, t0 = 0, time.perf_counter()
+        while True:
+            fn(); passes += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds and passes >= 3:
+                return n * passes / dt / 1e9, dt / passes * 1e6
+
+    out = {}
+    p, m, s = syn.ndt_problem(1_000_000, 1002, syn.CFG2_TRUE)
+    planes = oracle.simd_pack(p, m, s)
+    T = syn.CFG2_TRUE
+    for label, th in (("1_thread_as_reference", 1), ("all_threads", threads)):
+        g, us = rate(lambda: oracle.simd_ndt3_assemble(planes, len(p), np.eye(2), np.zeros(2), 2, [1.0], th), len(p))
+        out.setdefault("cfg2", {})[label] = {"gpoints_s": g, "us_per_iteration": us, "cores": th}
+    out["cfg2"].update({"kind": "port", "unit": "Gpoints/s", "value": out["cfg2"]["all_threads"]["gpoints_s"],
+                        "cores": threads,
+                        "sample": "%d correspondences of cfg2, float 8-lane planar twin (..._analytic_3dof_simd.cc:85-157 "
+                                  "restated), Huber(1.0), %s" % (len(p), flags)})
+    X, px, K = syn.pnp_problem(50_000, 1003)
+    planes = oracle.simd_reproj_pack(X, px)
+    for label, th in (("1_thread_as_reference", 1), ("all_threads", threads)):
+        g, us = rate(lambda: oracle.simd_reproj_assemble(planes, len(X), K, np.eye(3), np.zeros(3), 3, [1e-2], th),
+                     len(X))
+        out.setdefault("cfg3", {})[label] = {"gpoints_s": g, "us_per_iteration": us, "cores": th}
+    best = max(("1_thread_as_reference", "all_threads"), key=lambda k: out["cfg3"][k]["gpoints_s"])
+    out["cfg3"].update({"kind": "port", "unit": "Gpoints/s", "value": out["cfg3"][best]["gpoints_s"],
+                        "cores": out["cfg3"][best]["cores"],
+                        "sample": "%d correspondences of cfg3, float 8-lane reprojection twin (reprojection_error_minimizer_"
+                                  "analytic_simd.cc:55-137 restated, quirks kept), Cauchy(0.01), %s; value = the faster of "
+                                  "1 thread (as the reference runs it) and all threads" % (len(X), flags)})
+    return out
 
 
 def measure_batched(nlo, syn, ctx, rank, world, dist, num_problems=4096, points=20000, iters=40):
@@ -631,6 +791,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()
     global GUARD
     GUARD = StdoutGuard()

@@ -134,6 +134,21 @@ void nlo_oracle_simd_pack(int64_t n, const double* point, const double* mean,
 void nlo_oracle_simd_ndt6_assemble(int64_t n, const float* planes, const double R_rowmajor[9],
                                    const double t[3], int loss_kind, const double loss_params[2],
                                    int num_threads, double H21[21], double g[6], double* cost);
+/* float 8-lane twin of the planar minimizer (..._analytic_3dof_simd.cc:85-157) over floor(n/8)*8
+ * correspondences of the same 15 float planes.  The reference runs it on ONE thread; num_threads > 1
+ * applies the stride split of ..._analytic_simd.cc:55-76. */
+void nlo_oracle_simd_ndt3_assemble(int64_t n, const float* planes, const double R2_rowmajor[4],
+                                   const double t2[2], int loss_kind, const double loss_params[2],
+                                   int num_threads, double H6[6], double g[3], double* cost);
+/* float 8-lane twin of the reprojection minimizer
+ * (reprojection_error_minimizer/reprojection_error_minimizer_analytic_simd.cc:19-27 pack, :55-137 loop),
+ * with its quirks: ||r|| (not squared) goes to the loss, the gate is z > 0.  One thread in the
+ * reference; num_threads > 1 as above. */
+void nlo_oracle_simd_reproj_pack(int64_t n, const double* local_point, const double* pixel, float* planes);
+void nlo_oracle_simd_reproj_assemble(int64_t n, const float* planes, const double intrinsics[6],
+                                     const double R_rowmajor[9], const double t[3], int loss_kind,
+                                     const double loss_params[2], int num_threads, double H21[21],
+                                     double g[6], double* cost);
 /* scalar-double assembly on `num_threads` threads (..._analytic.cc:59-73,104-119). */
 void nlo_oracle_ndt6_assemble_threads(int64_t n, const double* point, const double* mean,
                                       const double* sqrt_info, const double R_rowmajor[9],

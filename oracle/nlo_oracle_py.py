@@ -300,3 +300,35 @@ def ndt6_assemble_threads(point, mean, sqrt_info, R, t, loss_kind=LOSS_NONE, los
                                            H.ctypes.data_as(_c_double_p),
                                            g.ctypes.data_as(_c_double_p), ctypes.byref(cost))
     return H, g, cost.value
+
+
+def simd_ndt3_assemble(planes, n, R2, t2, loss_kind=LOSS_NONE, loss_params=None, num_threads=1):
+    """Float 8-lane twin of the planar minimizer (..._analytic_3dof_simd.cc:85-157)."""
+    R2, Rp = _d(R2); t2, tp = _d(t2)
+    H = np.zeros(6); g = np.zeros(3); cost = ctypes.c_double(0)
+    pa = _params(loss_params)
+    lib().nlo_oracle_simd_ndt3_assemble(ctypes.c_int64(n), planes.ctypes.data_as(_c_float_p), Rp, tp,
+                                        ctypes.c_int(loss_kind), pa.ctypes.data_as(_c_double_p),
+                                        ctypes.c_int(num_threads), H.ctypes.data_as(_c_double_p),
+                                        g.ctypes.data_as(_c_double_p), ctypes.byref(cost))
+    return H, g, cost.value
+
+
+def simd_reproj_pack(local_point, pixel):
+    X, Xp = _d(local_point); px, pxp = _d(pixel)
+    n = X.size // 3
+    planes = np.zeros(5 * n, dtype=np.float32)
+    lib().nlo_oracle_simd_reproj_pack(ctypes.c_int64(n), Xp, pxp, planes.ctypes.data_as(_c_float_p))
+    return planes
+
+
+def simd_reproj_assemble(planes, n, intrinsics, R, t, loss_kind=LOSS_NONE, loss_params=None, num_threads=1):
+    """Float 8-lane twin of the reprojection minimizer (..._analytic_simd.cc:55-137), quirks kept."""
+    K, Kp = _d(intrinsics); R, Rp = _d(R); t, tp = _d(t)
+    H = np.zeros(21); g = np.zeros(6); cost = ctypes.c_double(0)
+    pa = _params(loss_params)
+    lib().nlo_oracle_simd_reproj_assemble(ctypes.c_int64(n), planes.ctypes.data_as(_c_float_p), Kp, Rp, tp,
+                                          ctypes.c_int(loss_kind), pa.ctypes.data_as(_c_double_p),
+                                          ctypes.c_int(num_threads), H.ctypes.data_as(_c_double_p),
+                                          g.ctypes.data_as(_c_double_p), ctypes.byref(cost))
+    return H, g, cost.value

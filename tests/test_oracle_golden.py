@@ -219,6 +219,35 @@ def test_simd_float_baseline_agrees_at_float_tolerance(oracle):
         np.testing.assert_allclose(got[2], ref[2], rtol=2e-3)
 
 
+def test_simd_planar_and_reprojection_baselines_agree_at_float_tolerance(oracle):
+    """The float twins timed beside cfg2 / cfg3 compute what the double paths compute (up to float
+    rounding and the reference's own quirks in the reprojection twin)."""
+    point, mean, S = syn.ndt_problem(20000, 1002, syn.CFG2_TRUE)
+    planes = oracle.simd_pack(point, mean, S)
+    T = syn.yaw_pose([0.01, -0.02, 0.0], 0.03)
+    for threads in (1, 3):
+        nT = 8 * ((len(point) // 8) // threads) * threads
+        ref = oracle.ndt3_assemble(point, mean, S, T[:2, :2], T[:2, 3], 2, [1.0], end=nT)
+        got = oracle.simd_ndt3_assemble(planes, len(point), T[:2, :2], T[:2, 3], 2, [1.0], num_threads=threads)
+        np.testing.assert_allclose(got[0], ref[0], rtol=2e-3, atol=1e-3 * np.abs(ref[0]).max())
+        np.testing.assert_allclose(got[1], ref[1], rtol=0, atol=2e-3 * np.abs(ref[0]).max())
+        np.testing.assert_allclose(got[2], ref[2], rtol=2e-3)
+    X, px, K = syn.pnp_problem(4000, 1003)
+    X[::9, 2] = -1.0                                  # behind the camera
+    planes = oracle.simd_reproj_pack(X, px)
+    R = syn.random_rotation(np.random.default_rng(6), 0.05); t = np.array([0.01, 0.02, -0.03])
+    n8 = (len(X) // 8) * 8
+    ref = oracle.reproj_assemble(X, px, K, R, t, 0, None, end=n8)
+    got = oracle.simd_reproj_assemble(planes, len(X), K, R, t, 0, None, num_threads=1)
+    np.testing.assert_allclose(got[0], ref[0], rtol=5e-3, atol=2e-3 * np.abs(ref[0]).max())
+    np.testing.assert_allclose(got[1], ref[1], rtol=0, atol=5e-3 * np.abs(ref[1]).max())
+    # the quirk: without a loss the twin's cost is sum ||r|| over ALL lanes, the gated ones included
+    Rq = R
+    Xw = X[:n8] @ Rq.T + t
+    r = np.stack([Xw[:, 0] / Xw[:, 2] - K[4] * (px[:n8, 0] - K[2]), Xw[:, 1] / Xw[:, 2] - K[5] * (px[:n8, 1] - K[3])], 1)
+    np.testing.assert_allclose(got[2], np.linalg.norm(r, axis=1).sum(), rtol=2e-3)
+
+
 @pytest.mark.timeout(300)
 def test_ndt_fixture_cost_band(oracle):
     """Reference fixture end to end (room -> 0.1 m voxel filter -> 1.0 m NDT map -> KD-tree
