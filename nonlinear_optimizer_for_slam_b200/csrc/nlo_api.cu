@@ -67,7 +67,8 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   memset(&p, 0, sizeof(p));
   for (int k = 0; k < pr->num_planes; ++k) p.planes[k] = pr->planes[k];
   p.partials = pr->d_partials;
-  p.sync_words = pr->d_sync;
+  p.ll_partials = pr->d_ll_partials;
+  p.ll_sums = pr->d_sync;
   p.loss_p0 = ctx->loss_params[0];
   p.loss_p1 = ctx->loss_params[1];
   for (int k = 0; k < 6; ++k) p.intrinsics[k] = pr->intrinsics[k];
@@ -78,6 +79,7 @@ IterParams BaseParams(nlo_context* ctx, nlo_problem* pr) {
   p.f32 = pr->f32 ? 1 : 0;
   p.stage_depth = ctx->stage_depth;
   p.debug_times = ctx->d_debug_times;
+  p.debug_all_ctas = ctx->debug_all_ctas ? 1 : 0;
   p.use_peer = (CommFor(ctx, pr) == kCommPeer) ? 1 : 0;
   p.peer = ctx->peer;
   return p;
@@ -112,6 +114,64 @@ int CheckPeerError(nlo_context* ctx, const nlo_problem* pr) {
   return NLO_OK;
 }
 
+// Shape of a persistent launch: CTAs per registration (a multiple of the cluster size), CTAs per
+// thread-block cluster, and whether every CTA gathers the cluster partials itself.
+struct GridPlan {
+  int gx = 1;
+  int cluster = 1;
+  int direct = 0;
+};
+
+// CTAs of this kernel variant that are co-resident in clusters of `cluster` (cached per context; a
+// device shared by several sub-contexts of one multi-device context is divided between them).
+int CoResidentCtas(nlo_context* ctx, const nlo_problem* pr, int kind, int cluster, bool resident) {
+  const int key = (((kind * 8 + ctx->loss_kind) * 2 + (pr->f32 ? 1 : 0)) * 16 + cluster) * 2 + (resident ? 1 : 0);
+  auto it = ctx->coresident.find(key);
+  if (it == ctx->coresident.end())
+    it = ctx->coresident.emplace(key, MaxCoResidentCtas(kind, ctx->loss_kind, pr->f32, cluster, resident)).first;
+  return it->second / std::max(1, ctx->device_share);
+}
+
+// `want` = CTAs per registration the caller would like (before the tile count and the cluster
+// granularity are taken into account), `rows` = registrations of the launch (gridDim.y).
+GridPlan PlanPersistentGrid(nlo_context* ctx, const nlo_problem* pr, int kind, int64_t tiles, int rows, int want,
+                            bool small, bool resident = false) {
+  GridPlan plan;
+  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(tiles, want));
+  const int64_t tiles_per_cta = (tiles + ctas - 1) / ctas;
+  for (int cluster = small ? ctx->cluster_small : ctx->cluster_big; cluster >= 1; cluster >>= 1) {
+    if (cluster > 1 && cluster > ctas) continue;  // no point in clusters of mostly idle CTAs
+    const int cap = (CoResidentCtas(ctx, pr, kind, cluster, resident) / std::max(1, rows) / cluster) * cluster;
+    if (cap < cluster) continue;
+    // idle CTAs in the last cluster are fine; a GPC that does not hold a whole number of clusters
+    // strands SMs, which is only acceptable while no CTA gets (noticeably) more tiles for it
+    const int gx = static_cast<int>(std::min<int64_t>((ctas + cluster - 1) / cluster * cluster, cap));
+    const int64_t with_cluster = (tiles + gx - 1) / gx;
+    if (cluster == 1 || with_cluster <= tiles_per_cta + tiles_per_cta / 32) {
+      plan.gx = gx;
+      plan.cluster = cluster;
+      break;
+    }
+  }
+  if (plan.gx < 1) plan.gx = 1;
+  plan.direct = (plan.gx > 1 && plan.gx / plan.cluster <= ctx->direct_max_clusters) ? 1 : 0;
+  return plan;
+}
+
+// Tag base of the next persistent launch on this problem: the solve epoch in the upper 16 bits, so
+// that LL words left by earlier solves never match.  When the epoch wraps the buffers are cleared.
+int NextEpoch(nlo_context* ctx, nlo_problem* pr, unsigned int* tag_base) {
+  pr->epoch += 1;
+  if (pr->epoch > 65535u) {
+    pr->epoch = 1;
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_ll_partials, 0, pr->ll_partials_bytes, ctx->stream));
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(pr->num_problems + 1) * kSyncStride * sizeof(unsigned long long),
+                                  ctx->stream));
+  }
+  *tag_base = pr->epoch << 16;
+  return NLO_OK;
+}
+
 // Enqueue the device-resident loop of one solve on the context stream.
 int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options& opt,
                 bool with_trace, int num_problems, int64_t begin_abs, int64_t end_abs) {
@@ -127,41 +187,64 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
   const int comm = CommFor(ctx, pr);
   const int64_t tiles = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
   const bool in_cta_loop = (comm == kCommNone) && (pr->batched || tiles <= kInCtaTiles);
-  if (pr->batched && ctx->use_persistent && tiles > kInCtaTiles && 2 * num_problems <= ctx->grid_single) {
+  const bool tags_fit = opt.max_iterations < 65535;  // the iteration number shares the 32-bit LL tag with the solve epoch
+  if (pr->batched && ctx->use_persistent && tags_fit && tiles > kInCtaTiles && 2 * num_problems <= ctx->grid_single) {
     // A small batch: one CTA per registration would leave most SMs idle, so every registration
     // gets G = (2 x SMs) / B CTAs of ONE persistent cooperative grid (gridDim.y = registrations),
-    // each with its own leader CTA, arrival counter and published state.
-    const int gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ctx->grid_single / num_problems, tiles)));
-    IterParams q = p;
-    q.mode = kModeSolve;
-    q.persistent = 1;
-    q.iterations_in_kernel = opt.max_iterations;
-    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(num_problems) * kSyncStride * sizeof(unsigned long long),
-                                  ctx->stream));
-    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, q, gx, num_problems, ctx->stream);
-    if (ce == cudaSuccess) return NLO_OK;
-    if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
-      return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
-    cudaGetLastError();  // not co-resident right now: fall through to one CTA per registration
+    // each registration with its own clusters, partial slots and state.
+    const GridPlan plan = PlanPersistentGrid(ctx, pr, kind, tiles, num_problems, ctx->grid_single / num_problems, true);
+    if (plan.gx > 1) {
+      IterParams q = p;
+      q.mode = kModeSolve;
+      q.persistent = 1;
+      q.iterations_in_kernel = opt.max_iterations;
+      q.gather_direct = plan.direct;
+      const int rc = NextEpoch(ctx, pr, &q.tag_base);
+      if (rc != NLO_OK) return rc;
+      const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, q, plan.gx, num_problems, plan.cluster, ctx->stream);
+      if (ce == cudaSuccess) return NLO_OK;
+      if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+        return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
+      cudaGetLastError();  // not co-resident right now: fall through to one CTA per registration
+    }
   }
   if (in_cta_loop) {
     // whole loop inside one CTA per registration: a single launch
     p.mode = kModeSolve;
     p.iterations_in_kernel = opt.max_iterations;
-    NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, ctx->stream));
+    NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, 1, ctx->stream));
     return NLO_OK;
   }
   const int grid_x = GridFor(ctx, begin_abs, end_abs);
-  if (UsePersistent(ctx, pr)) {
-    // persistent cooperative grid: the whole loop in ONE launch, one grid barrier per iteration.
-    // An empty shard (a rank that owns no points) still launches one CTA: it takes part in the
-    // all-reduce with zero sums.
-    int gx = grid_x;
-    if (tiles < 4LL * ctx->grid_single)
-      gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, ctx->grid_small)));
+  if (UsePersistent(ctx, pr) && tags_fit && ctx->use_resident && !pr->f32) {
+    // Latency-bound registration: if its tiles fit the shared memory of one CTA per SM they are
+    // loaded once and the whole loop runs in the resident kernel.
+    const GridPlan plan = PlanPersistentGrid(ctx, pr, kind, tiles, 1, ctx->sm_count / std::max(1, ctx->device_share), true, true);
+    const int64_t stages = (tiles + plan.gx - 1) / plan.gx;
+    if (stages <= ResidentMaxStages(kind)) {
+      IterParams q = p;
+      q.mode = kModeSolve;
+      q.persistent = 1;
+      q.iterations_in_kernel = opt.max_iterations;
+      q.gather_direct = (comm == kCommNone) ? plan.direct : 0;
+      const int rc = NextEpoch(ctx, pr, &q.tag_base);
+      if (rc != NLO_OK) return rc;
+      const cudaError_t ce = LaunchResident(kind, ctx->loss_kind, q, plan.gx, 1, plan.cluster, static_cast<int>(stages), ctx->stream);
+      if (ce == cudaSuccess) return NLO_OK;
+      if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+        return Fail(ctx, NLO_ECUDA, std::string("cooperative launch (resident): ") + cudaGetErrorString(ce));
+      cudaGetLastError();  // not co-resident right now: the streaming kernel below
+    }
+  }
+  if (UsePersistent(ctx, pr) && tags_fit) {
+    // persistent cooperative grid: the whole loop in ONE launch.  An empty shard (a rank that owns
+    // no points) still launches one CTA: it takes part in the all-reduce with zero sums.
+    const bool small = tiles < 4LL * ctx->grid_single;
+    const GridPlan plan = PlanPersistentGrid(ctx, pr, kind, tiles, 1, small ? ctx->grid_small : ctx->grid_single, small);
     p.mode = kModeSolve;
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
+    p.gather_direct = (comm == kCommNone) ? plan.direct : 0;
     // Streaming a large scan runs fastest with 3 tiles in flight per CTA (measured on B200, fp64 NDT,
     // 64M points: depth 2 / 3 / 4 = 71.3 / 75.9 / 71.3 Gpoints/s); the batched one-CTA-per-registration
     // shape keeps all 4 allocated stages.
@@ -172,8 +255,9 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
       if (ctx->l2_keep_mb > 0.0 && scan_mb > ctx->l2_policy_min_mb && opt.max_iterations > 1)
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
     }
-    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, kSyncStride * sizeof(unsigned long long), ctx->stream));
-    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, ctx->stream);
+    const int rc = NextEpoch(ctx, pr, &p.tag_base);
+    if (rc != NLO_OK) return rc;
+    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, plan.gx, 1, plan.cluster, ctx->stream);
     if (ce == cudaSuccess) return NLO_OK;
     if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
       return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
@@ -182,6 +266,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     p.persistent = 0;
     p.iterations_in_kernel = 1;
     p.l2_keep_tiles = 0;
+    p.gather_direct = 0;
   }
   // One launch per iteration.  A batched problem only gets here when its cooperative launch was
   // refused; its registrations then run one CTA each (the partial buffer is sized for one grid row).
@@ -189,14 +274,14 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
   for (int it = 0; it < opt.max_iterations; ++it) {
     if (comm == kCommNccl) {
       p.mode = kModeAssemble;
-      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx_loop, num_problems, ctx->stream));
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx_loop, num_problems, 1, ctx->stream));
       const int rc = NcclAllReduceSums(ctx, pr->d_sums);
       if (rc != NLO_OK) return rc;
       p.mode = kModeStepOnly;
-      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, ctx->stream));
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, 1, num_problems, 1, ctx->stream));
     } else {
       p.mode = kModeSolve;
-      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx_loop, num_problems, ctx->stream));
+      NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, gx_loop, num_problems, 1, ctx->stream));
     }
   }
   return NLO_OK;
@@ -324,6 +409,10 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   // grid_single CTAs, a small batch num_problems x (grid_single / num_problems) <= grid_single
   NLO_CUDA_P(cudaMalloc(&pr->d_partials,
                         2 * static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double)));
+  // cluster partials of the persistent path as LL words: [2 parities][<= grid_single clusters][28][2]
+  pr->ll_partials_bytes = 2 * static_cast<size_t>(std::max(ctx->grid_single, 1) + kMaxCluster) * kAcc6 * 2 * sizeof(unsigned long long);
+  NLO_CUDA_P(cudaMalloc(&pr->d_ll_partials, pr->ll_partials_bytes));
+  NLO_CUDA_P(cudaMemsetAsync(pr->d_ll_partials, 0, pr->ll_partials_bytes, ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_sync, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long), ctx->stream));
   NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
@@ -367,7 +456,7 @@ int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index,
   p.sums = pr->d_sums + 32 * slot;
   p.mode = kModeAssemble;
   const int grid_x = GridFor(ctx, hr->begin, hr->end);
-  NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, 1, ctx->stream));
+  NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, 1, 1, ctx->stream));
   if (comm == kCommNccl) {
     const int rc = NcclAllReduceSums(ctx, pr->d_sums + 32 * slot);
     if (rc != NLO_OK) return rc;
@@ -454,16 +543,36 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
   float ms = 0.f;
   NLO_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   if (ctx->d_debug_times != nullptr && options->max_iterations >= 8 && options->max_iterations <= kDebugIterations) {
-    std::vector<unsigned long long> ts(kDebugIterations * 8);
+    std::vector<unsigned long long> ts(kDebugIterations * kDebugSlots);
     cudaMemcpy(ts.data(), ctx->d_debug_times, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    // average phase durations over iterations 2..7 (ns): tiles | cta-sync | barrier | x-cta sum | step | sync
+    // average phase durations over iterations 2..7 (ns), CTA 0: tiles | CTA sync | cluster pre-reduction + LL store |
+    // gather of the cluster partials | canonical + [exchange] + step | CTA sync
     double acc[6] = {0, 0, 0, 0, 0, 0};
     double period = 0;
     for (int it = 2; it < 8; ++it) {
-      for (int k = 0; k < 6; ++k) acc[k] += static_cast<double>(ts[it * 8 + k + 1]) - static_cast<double>(ts[it * 8 + k]);
-      period += static_cast<double>(ts[(it + 1) * 8]) - static_cast<double>(ts[it * 8]);
+      for (int k = 0; k < 6; ++k)
+        acc[k] += static_cast<double>(ts[it * kDebugSlots + k + 1]) - static_cast<double>(ts[it * kDebugSlots + k]);
+      period += static_cast<double>(ts[(it + 1) * kDebugSlots]) - static_cast<double>(ts[it * kDebugSlots]);
     }
-    fprintf(stderr, "[nlo debug] ns/iter: tiles %.0f | cta-sync %.0f | barrier %.0f | x-cta-sum %.0f | canon+step %.0f | sync %.0f | period %.0f\n",
+    if (ctx->debug_all_ctas && getenv("NLO_DEBUG_FILE") != nullptr) {
+      std::vector<unsigned long long> all(static_cast<size_t>(kDebugCtas) * kDebugIterations * kDebugSlots);
+      cudaMemcpy(all.data(), ctx->d_debug_times, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(getenv("NLO_DEBUG_FILE"), "wb")) {
+        fwrite(all.data(), sizeof(unsigned long long), all.size(), f);
+        fclose(f);
+      }
+      cudaMemset(ctx->d_debug_times, 0, all.size() * sizeof(unsigned long long));
+    }
+    {
+      // sub-phases relative to stamp 2 (the CTA sync after the tiles)
+      double sub[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int it = 2; it < 8; ++it)
+        for (int k = 0; k < 7; ++k)
+          sub[k] += static_cast<double>(ts[it * kDebugSlots + 8 + k]) - static_cast<double>(ts[it * kDebugSlots + 2]);
+      fprintf(stderr, "[nlo debug] ns after cta-sync: reduce-entry %.0f | (9) %.0f | canonical-done %.0f | reduce-returned %.0f | step-entry %.0f | stepped %.0f | state-out %.0f\n",
+              sub[0] / 6, sub[1] / 6, sub[2] / 6, sub[3] / 6, sub[4] / 6, sub[5] / 6, sub[6] / 6);
+    }
+    fprintf(stderr, "[nlo debug] ns/iter: tiles %.0f | cta-sync %.0f | cluster+ll %.0f | gather %.0f | canon+xchg+step %.0f | sync %.0f | period %.0f\n",
             acc[0] / 6, acc[1] / 6, acc[2] / 6, acc[3] / 6, acc[4] / 6, acc[5] / 6, period / 6);
   }
   int rc_all = NLO_OK;
@@ -530,14 +639,29 @@ int nlo_context_create(int device, nlo_context** out) {
   if (menv != nullptr) ctx->l2_policy_min_mb = atof(menv);
   const char* senv = getenv("NLO_STAGE_DEPTH");
   if (senv != nullptr) ctx->stage_depth = atoi(senv);
-  const char* cenv = getenv("NLO_CLUSTER");
-  if (cenv != nullptr) ctx->cluster_size = atoi(cenv);
+  // Thread-block clusters of the persistent path (DSMEM pre-reduction of the per-CTA sums): CTAs per
+  // cluster for problems that live in shared memory / L2 and for streamed scans, and the number of
+  // cluster partials up to which every CTA gathers them itself.
+  auto env_int = [](const char* name, int fallback, int lo, int hi) {
+    const char* v = getenv(name);
+    if (v == nullptr) return fallback;
+    return std::max(lo, std::min(hi, atoi(v)));
+  };
+  auto pow2_floor = [](int v) { int p2 = 1; while (2 * p2 <= v) p2 *= 2; return p2; };
+  ctx->cluster_small = pow2_floor(env_int("NLO_CLUSTER", 4, 1, kMaxCluster));
+  ctx->cluster_big = pow2_floor(env_int("NLO_CLUSTER_BIG", 2, 1, kMaxCluster));
+  ctx->direct_max_clusters = env_int("NLO_DIRECT_MAX", 48, 0, 1 << 20);
+  ctx->use_resident = env_int("NLO_NO_RESIDENT", 0, 0, 1) == 0;
   const char* tenv = getenv("NLO_INGEST_THREADS");
   if (tenv != nullptr) ctx->ingest_threads = atoi(tenv);
   const char* denv = getenv("NLO_DEBUG_TIMES");
-  if (denv != nullptr && denv[0] == '1') {
-    cudaMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), kDebugIterations * 8 * sizeof(unsigned long long));
-    cudaMemset(ctx->d_debug_times, 0, kDebugIterations * 8 * sizeof(unsigned long long));
+  if (denv != nullptr && (denv[0] == '1' || denv[0] == '2')) {
+    // 1: phases of CTA 0 printed to stderr after every solve; 2: stamps of every CTA also written to
+    // $NLO_DEBUG_FILE (raw u64 [kDebugCtas][kDebugIterations][8], slot 7 of iteration 0 = SM id)
+    ctx->debug_all_ctas = denv[0] == '2';
+    const size_t bytes = static_cast<size_t>(kDebugCtas) * kDebugIterations * kDebugSlots * sizeof(unsigned long long);
+    cudaMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), bytes);
+    cudaMemset(ctx->d_debug_times, 0, bytes);
   }
   const char* genv = getenv("NLO_GRID");
   if (genv != nullptr && atoi(genv) > 0) ctx->grid_single = atoi(genv);
@@ -684,6 +808,7 @@ int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
   cudaFree(pr->d_partials);
   cudaFree(pr->d_tickets);
   cudaFree(pr->d_sync);
+  cudaFree(pr->d_ll_partials);
   cudaFree(pr->d_sums);
   cudaFree(pr->d_poses);
   cudaFree(pr->d_results);

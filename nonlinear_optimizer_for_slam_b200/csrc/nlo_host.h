@@ -90,7 +90,12 @@ struct nlo_context {
   double l2_keep_mb = 0.0;        // NLO_L2_KEEP_MB: bytes of a re-read scan pinned in L2 (0 = off)
   double l2_policy_min_mb = 0.0;  // only scans larger than this get an explicit policy
   int grid_small = 0;             // CTAs of the persistent path for L2-resident problems
-  int cluster_size = 0;           // NLO_CLUSTER: CTAs per thread-block cluster of the persistent path (0 = default)
+  int cluster_small = 4;          // NLO_CLUSTER: CTAs per thread-block cluster, problems resident in smem / L2
+  int cluster_big = 2;            // NLO_CLUSTER_BIG: the same for streamed scans (must not strand SMs)
+  int direct_max_clusters = 48;   // NLO_DIRECT_MAX: up to this many cluster partials every CTA gathers them itself
+  bool use_resident = true;       // NLO_NO_RESIDENT=1: latency-bound registrations also run the streaming kernel
+  int device_share = 1;           // sub-contexts of one multi-device context that sit on this device
+  std::map<int, int> coresident;  // (kernel variant, cluster size) -> co-resident CTAs on this device
   // communicator
   int comm_kind = nlo::kCommNone;
   bool comm_suspended = false;  // nlo_comm_suspend: calls behave as if no communicator were attached
@@ -105,7 +110,8 @@ struct nlo_context {
   int* d_peer_error = nullptr;
   nlo_problem* reg_workspace = nullptr;  // correspondences of nlo_ndt_register: kept across scans,
   int64_t reg_workspace_capacity = 0;    // grown on demand (no per-frame allocation)
-  unsigned long long* d_debug_times = nullptr;  // NLO_DEBUG_TIMES=1: [64][8] stamps of the last loop
+  unsigned long long* d_debug_times = nullptr;  // NLO_DEBUG_TIMES=1|2: [kDebugCtas][64][8] stamps of the last loop
+  bool debug_all_ctas = false;
   int generation = 0;  // bumped whenever cached graphs become stale (loss / comm change)
   // ingest pipeline
   nlo::IngestRing ring;
@@ -135,7 +141,10 @@ struct nlo_problem {
   nlo::State* d_states = nullptr;  // [num_problems + 1]
   double* d_partials = nullptr;
   unsigned int* d_tickets = nullptr;     // [num_problems + 1]
-  unsigned long long* d_sync = nullptr;  // [num_problems + 1][kSyncStride] persistent-path counter + LL state
+  unsigned long long* d_sync = nullptr;  // [num_problems + 1][kSyncStride] persistent path: canonical sums as LL words
+  unsigned long long* d_ll_partials = nullptr;  // persistent path: cluster partials as LL words
+  size_t ll_partials_bytes = 0;
+  unsigned int epoch = 0;                // persistent launches made on this problem (mod 65535): upper half of the LL tags
   double* d_sums = nullptr;              // [(num_problems + 1) * 32]
   double* d_poses = nullptr;             // [(num_problems + 1) * 16]
   double* d_results = nullptr;           // [(num_problems + 1) * 4]

@@ -19,9 +19,12 @@ constexpr int kReprojPlanes = 5;      // X Y Z | u v
 constexpr int kAcc6 = 28;             // 21 H + 6 g + cost
 constexpr int kAcc3 = 10;             // 6 H + 3 g + cost
 constexpr int kMaxRanks = 8;
-constexpr int kSyncStride = 8 + 64;    // 8-byte words per registration of IterParams::sync_words
 constexpr int kPeerWords = 64;        // 8-byte words per (parity, source rank) slot of the peer exchange
-constexpr int kDebugIterations = 64;  // rows of IterParams::debug_times
+constexpr int kSyncStride = 2 * kPeerWords;  // 8-byte words per registration of IterParams::ll_sums: [2 parities][kPeerWords]
+constexpr int kMaxCluster = 8;        // CTAs per thread-block cluster of the persistent path (portable limit)
+constexpr int kDebugIterations = 64;  // iterations stamped in IterParams::debug_times
+constexpr int kDebugSlots = 16;       // stamps per iteration: 0-6 phases of the kernel, 7 SM id, 8-14 sub-phases
+constexpr int kDebugCtas = 320;       // CTAs stamped when every CTA is (NLO_DEBUG_TIMES=2)
 // Spin-wait limits (a wait that expires ends the solve with status 2 / NLO_ETIMEOUT or NLO_ECOMM, never a
 // hang).  The leader CTA may legitimately sit in the peer exchange for as long as another rank needs to
 // reach its own Solve (ingest skew, lazy module load, a time-sliced GPU), and the other CTAs of the grid
@@ -81,8 +84,16 @@ struct IterParams {
   State* states;        // [num_problems]
   double* partials;     // [2 parities][num_problems][grid.x][nacc]
   unsigned int* tickets;  // [num_problems] last-CTA election of the one-iteration-per-launch path
-  unsigned long long* sync_words;  // persistent path, per registration kSyncStride words (zeroed at launch):
-                                   // word 0 = arrival counter (u32), words 8.. = the published state as LL words
+  // Persistent path ("LL" words: 32 payload bits + a 32-bit tag per 8-byte store, valid the moment the tag
+  // matches -- no fence, no flag, no counter):
+  unsigned long long* ll_partials;  // [2 parities][num_problems][clusters per registration][nacc][2 words]: the
+                                    // raw sums of one thread-block cluster, written by its rank-0 CTA
+  unsigned long long* ll_sums;      // [num_problems][2 parities][kPeerWords]: the canonical sums of the whole
+                                    // registration, written by CTA 0 when the CTAs do not gather the partials
+                                    // themselves (gather_direct == 0, single GPU)
+  unsigned int tag_base;            // tag of iteration `it` = tag_base + it + 1 (solve epoch in the upper 16 bits)
+  int gather_direct;                // every CTA gathers the cluster partials and steps on its own (few clusters);
+                                    // 0: CTA 0 gathers, [pushes to the peers], every CTA gathers ll_sums / peer slots
   double* sums;           // [num_problems][32] canonical H|g|cost (out for assemble, in for step-only)
   double* trace;          // nullable: [num_problems][max_iterations][trace_width]
   double loss_p0, loss_p1;
@@ -92,7 +103,9 @@ struct IterParams {
   int iterations_in_kernel;  // > 1 only when grid.x == 1 (whole loop inside one CTA)
   int mode;
   int use_peer;
-  unsigned long long* debug_times;  // nullable: [iterations][8] globaltimer stamps of CTA 0 (profiling aid)
+  unsigned long long* debug_times;  // nullable: [CTA][iterations][8] globaltimer stamps (profiling aid; CTA 0 only
+                                    // unless debug_all_ctas)
+  int debug_all_ctas;
   long long l2_keep_tiles;  // > 0: tiles [0, l2_keep_tiles) of the range are loaded evict_last, the rest evict_first
   int stage_depth;  // > 0: use only this many of the allocated shared-memory stages
   int f32;  // NDT planes stored as float (fp32 storage, fp64 math); planes[0] then points at float data
@@ -101,8 +114,15 @@ struct IterParams {
 };
 
 // Launchers (nlo_kernels.cu).  grid_x CTAs per registration, num_problems registrations.
+// `cluster` CTAs per thread-block cluster (1 = none; grid_x must be a multiple of it).
 cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
-                            cudaStream_t stream);
+                            int cluster, cudaStream_t stream);
+int MaxCoResidentCtas(int kind, int loss, bool f32, int cluster, bool resident);
+// Resident kernel: the whole registration lives in the shared memory of the grid, `stages` tiles per CTA
+// (<= ResidentMaxStages(kind)); always a persistent cooperative launch of the complete loop.
+cudaError_t LaunchResident(int kind, int loss, const IterParams& p, int grid_x, int num_problems, int cluster,
+                           int stages, cudaStream_t stream);
+int ResidentMaxStages(int kind);
 cudaError_t ConfigureKernels();
 size_t IterationSmemBytes(int kind);
 

@@ -25,6 +25,7 @@
 // and their SIMD / thread-pool twins (..._analytic_simd.cc:55-76,114-177).
 #include <climits>
 #include <cstdio>
+#include <cstring>
 
 #include "nlo_device.cuh"
 
@@ -122,6 +123,19 @@ __host__ __device__ constexpr int PlanesOf() {
   return KIND == kReproj ? kReprojPlanes : kNdtPlanes;
 }
 
+// Shared memory of the reduction / exchange / step phase of an iteration (the same for every kind).
+struct ReduceArea {
+  double warp_sums[8][kAcc6];     // sums of the 8 consumer warps
+  double gather_lanes[8][kAcc6];  // the 8 strided lanes of a cross-CTA / cross-cluster / cross-rank sum
+  double cluster_part[2][kMaxCluster][kAcc6];  // rank-0 CTA of a cluster: the sums of its CTAs (by iteration parity)
+  double total[32];               // reduced (raw, then canonical) sums
+  State state;                    // CTA-local copy of the registration state
+  unsigned long long seq0;        // peer exchange sequence number at kernel start
+  int exchanges;                  // peer exchanges made by this kernel (thread 0's bookkeeping)
+  int flag;
+  int fail;                       // a polled wait expired
+};
+
 // ST = storage type of the planes in HBM and in the stages: double (parity mode, 96 B per NDT
 // correspondence) or float (fp32 storage, fp64 math: 48 B; twice the stages fit the same smem).
 template <int KIND, typename ST>
@@ -134,13 +148,9 @@ struct SmemLayout {
 #endif
   static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? NLO_NDT_STAGES : 8);
   ST stages[kStages][PlanesOf<KIND, ST>()][kTile];
-  double warp_sums[8][kAcc6];  // 8 consumer warps, or 8 strided lanes of the cross-CTA sum
-  double total[32];            // reduced (raw, then canonical) sums
-  State state;                 // CTA-local copy of the registration state
+  ReduceArea red;
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  unsigned int halves[kPeerWords];  // payload halves of the published state (LL words)
-  int flag;
 };
 
 template <int KIND, typename ST = double>
@@ -148,58 +158,332 @@ constexpr size_t SmemBytes() {
   return sizeof(SmemLayout<KIND, ST>);
 }
 
-// One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
-// finalising CTA.  "LL" wire format: every 8-byte word carries 4 bytes of payload and the 4-byte
-// sequence number of the exchange, so a word is valid the moment its sequence matches -- one
-// NVLink one-way latency, no fences, no separate flag.  A double travels as two words.  Slots are
-// double-buffered by sequence parity (a rank can only be one exchange ahead of a peer).  The sum
-// runs in rank order 0..n-1 on every rank => bit-identical results everywhere.
-__device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc) {
-  __shared__ unsigned int halves[kMaxRanks][kPeerWords];
+// ------------------------------------------------------------------ thread-block cluster helpers
+__device__ __forceinline__ unsigned int ClusterCtaRank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int ClusterIdX() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int ClusterCountX() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int ClusterSize() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// Hardware barrier of the cluster; release / acquire orders the distributed-shared-memory stores
+// made before it against the loads made after it.
+__device__ __forceinline__ void ClusterSync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Stores `v` at the address `local` has in the shared memory of CTA `target_rank` of this cluster.
+__device__ __forceinline__ void StoreClusterF64(double* local, unsigned int target_rank, double v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(SmemAddr(local)), "r"(target_rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// ------------------------------------------------------------------ "LL" words
+// A double travels as two 8-byte words, each = (tag << 32) | 32 payload bits, so that a word is
+// valid the moment its tag matches: one store, one (polled) load, no fence, no separate flag --
+// one L2 round trip inside a GPU, one NVLink one-way latency between GPUs.  The two words of a
+// double are adjacent (one 16-byte store / load; each half is validated on its own).
+__device__ __forceinline__ void StoreLL(unsigned long long* dst, double v, unsigned int tag) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
+  const unsigned long long lo = t | (bits & 0xffffffffULL), hi = t | (bits >> 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void LoadLL(const unsigned long long* src, unsigned long long& lo,
+                                       unsigned long long& hi) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+}
+
+// Fixed-order sum of `n_src` LL records of NACC doubles (record c at base + c * stride_words):
+// thread (j, l8) polls value j of records l8, l8+8, ... -- up to 8 loads in flight per thread --
+// and adds them in record order, then the 8 lanes are added in lane order.  total[0..NACC) is
+// written by threads 0..NACC-1 (warp 0) after an internal __syncthreads; *fail is set when a
+// record did not show up within `timeout_ns`.  Called by all threads of the CTA.
+template <int NACC>
+__device__ __forceinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
+                                         unsigned int tag, unsigned long long timeout_ns,
+                                         double (*lanes)[kAcc6], double* total, int* fail) {
   const int tid = threadIdx.x;
-  const unsigned long long seq = *pc.seq + 1;
-  const unsigned int seq32 = static_cast<unsigned int>(seq);
-  const int parity = static_cast<int>(seq & 1ULL);
-  const int words = 2 * nacc;
-  if (tid < words) {
-    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(total[tid >> 1]));
-    const unsigned long long half = (tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
-    const unsigned long long word = (static_cast<unsigned long long>(seq32) << 32) | half;
-    const int slot = (parity * kMaxRanks + pc.rank) * kPeerWords + tid;
-    for (int r = 0; r < pc.nranks; ++r)
-      *reinterpret_cast<volatile unsigned long long*>(pc.slots[r] + slot) = word;
-    const unsigned long long start = GlobalTimerNs();
-    for (int r = 0; r < pc.nranks; ++r) {
-      const volatile unsigned long long* src =
-          reinterpret_cast<const volatile unsigned long long*>(pc.slots[pc.rank]) +
-          (parity * kMaxRanks + r) * kPeerWords + tid;
-      unsigned long long w = *src;
-      while (static_cast<unsigned int>(w >> 32) != seq32) {
-        if (GlobalTimerNs() - start > kPeerTimeoutNs) {  // a peer died; fail instead of hanging
-          *pc.error = 1;
-          break;
-        }
-        w = *src;
+  const int j = tid >> 3, l8 = tid & 7;
+  if (j < NACC) {
+    double s = 0.0;
+    unsigned long long start = 0ULL;
+    for (int c0 = l8; c0 < n_src; c0 += 64) {
+      unsigned long long lo[8], hi[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 8 * u;
+        if (c < n_src) LoadLL(base + static_cast<size_t>(c) * stride_words + 2 * j, lo[u], hi[u]);
       }
-      halves[r][tid] = static_cast<unsigned int>(w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 8 * u;
+        if (c < n_src) {
+          while (static_cast<unsigned int>(lo[u] >> 32) != tag || static_cast<unsigned int>(hi[u] >> 32) != tag) {
+            if (start == 0ULL) start = GlobalTimerNs();
+            if (GlobalTimerNs() - start > timeout_ns) {
+              *fail = 1;
+              lo[u] = hi[u] = static_cast<unsigned long long>(tag) << 32;
+              break;
+            }
+            LoadLL(base + static_cast<size_t>(c) * stride_words + 2 * j, lo[u], hi[u]);
+          }
+          s += __longlong_as_double(static_cast<long long>((hi[u] << 32) | (lo[u] & 0xffffffffULL)));
+        }
+      }
     }
+    lanes[l8][j] = s;
   }
   __syncthreads();
-  if (tid < nacc) {
+  if (tid < NACC) {
     double s = 0.0;
-    for (int r = 0; r < pc.nranks; ++r) {
-      const unsigned long long bits = (static_cast<unsigned long long>(halves[r][2 * tid + 1]) << 32) |
-                                      static_cast<unsigned long long>(halves[r][2 * tid]);
-      s += __longlong_as_double(static_cast<long long>(bits));
-    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += lanes[w][tid];
     total[tid] = s;
   }
-  if (tid == 0) *pc.seq = seq;
-  __syncthreads();
+}
+
+// profiling aid (NLO_DEBUG_TIMES=1): CTA 0 / thread 0 stamps the phases of each iteration
+// (NLO_DEBUG_TIMES=2: every CTA of the first registration, rows [CTA][iteration][8])
+#define NLO_STAMP(slot)                                                                         \
+  do {                                                                                          \
+    if (p.debug_times != nullptr && blockIdx.y == 0 && threadIdx.x == 0 && it < kDebugIterations && \
+        (blockIdx.x == 0 || (p.debug_all_ctas && blockIdx.x < kDebugCtas)))                     \
+      p.debug_times[(static_cast<size_t>(blockIdx.x) * kDebugIterations + it) * kDebugSlots + (slot)] = GlobalTimerNs(); \
+  } while (0)
+
+enum ReduceOutcome : int {
+  kReduceStep = 0,     // red.total holds the canonical sums of the whole registration: step
+  kReduceLeave = 1,    // this CTA is done with the launch (not the last one of a one-iteration launch)
+  kReduceFailed = 2,   // a polled wait expired
+  kReduceAssembled = 3 // assemble mode: the sums were written out
+};
+
+// Everything between the tile loop and the damped step of iteration `it`: CTA sum, cluster
+// pre-reduction over distributed shared memory, LL-format cluster partials, their gather, the
+// rotation to the canonical frame and -- sharded across GPUs, or when CTA 0 gathers on behalf of
+// the grid -- the exchange of the canonical sums.
+template <int KIND>
+__device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterParams& p, int it) {
+  constexpr int NACC = KindTraits<KIND>::kAcc;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int problem = blockIdx.y;
+  const int grid_x = gridDim.x;
+  const bool writer = (blockIdx.x == 0) || !p.persistent;
+  State& st = red.state;
+  NLO_STAMP(8);
+
+  // CTA sum over the 8 consumer warps, fixed order; thread k < NACC (warp 0) owns value k
+  double cta_sum = 0.0;
+  if (tid < NACC) {
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) cta_sum += red.warp_sums[w][tid];
+  }
+  if (grid_x == 1) {
+    if (tid < NACC) red.total[tid] = cta_sum;
+    NLO_STAMP(3);
+  } else if (p.persistent) {
+    // Persistent grid.  No counter, no fence, no leader round trip:
+    //  1. the CTAs of a thread-block cluster hand their 28 sums to the cluster's rank-0 CTA through
+    //     distributed shared memory and meet at the hardware cluster barrier; rank 0 adds them in
+    //     rank order and stores the cluster's partial as "LL" words (32 payload bits + the tag of
+    //     this iteration per 8-byte store: a word is valid the moment its tag matches);
+    //  2. gather_direct (few clusters): EVERY CTA polls all cluster partials, adds them in cluster
+    //     order and performs the identical step on its own copy of the state -- one L2 round trip
+    //     between the last partial and the new pose everywhere.  Otherwise CTA 0 gathers, rotates
+    //     to the canonical frame and writes the sums (LL again) to the local slot -- or, sharded
+    //     across GPUs, into the slot of every rank over NVLink -- and every CTA polls those.
+    // The cluster this CTA belongs to is 1 x 1 x 1 when the launch carries no cluster attribute.
+    const unsigned int csize = ClusterSize(), crank = ClusterCtaRank();
+    const int n_clusters = static_cast<int>(ClusterCountX()), cluster_id = static_cast<int>(ClusterIdX());
+    const int parity = it & 1;
+    const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;
+    unsigned long long* row_partials =
+        p.ll_partials + static_cast<size_t>(parity * gridDim.y + problem) * n_clusters * (2 * NACC);
+    if (csize > 1) {
+      if (tid < NACC) StoreClusterF64(&red.cluster_part[parity][crank][tid], 0u, cta_sum);
+      ClusterSync();
+      if (crank == 0 && tid < NACC) {
+        cta_sum = 0.0;
+        for (unsigned int r = 0; r < csize; ++r) cta_sum += red.cluster_part[parity][r][tid];
+      }
+    }
+    if (crank == 0 && tid < NACC)
+      StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag);
+    NLO_STAMP(3);
+    if (p.gather_direct || blockIdx.x == 0)
+      GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, kGridTimeoutNs, red.gather_lanes, red.total, &red.fail);
+  } else {
+    // one launch per iteration: per-CTA partial -> HBM/L2, the last CTA to arrive (ticket) sums
+    double* partial_base = p.partials + static_cast<size_t>(problem) * grid_x * NACC;
+    if (tid < NACC) {
+      __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, cta_sum);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
+      red.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
+      if (red.flag) p.tickets[problem] = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (red.flag == 0) return kReduceLeave;  // only the last CTA to arrive carries on
+    __threadfence();
+    NLO_STAMP(3);
+    // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
+    const int j = tid >> 3, l8 = tid & 7;
+    if (j < NACC) {
+      const double* base = partial_base + j;
+      double s = 0.0;
+      // loads are issued 16 at a time (independent addresses, the tail predicated so that it
+      // costs one round trip instead of one per element); the adds keep the fixed order
+      for (int g = l8; g < grid_x; g += 128) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = g + 8 * u;
+          v[u] = c < grid_x ? __ldcg(base + static_cast<size_t>(c) * NACC) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
+      red.gather_lanes[l8][j] = s;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red.gather_lanes[w][tid];
+      red.total[tid] = s;
+    }
+  }
+  NLO_STAMP(4);
+  // raw -> canonical (needs the R the sums were taken at): 28 lanes of warp 0, which also hold
+  // red.total.  CTAs that did not gather (they wait for CTA 0's sums below) skip it.
+  const bool grid_exchange = p.persistent && grid_x > 1 && !p.gather_direct;
+  const bool has_total = !grid_exchange || blockIdx.x == 0;
+  if (KIND != kNdt3 && warp == 0 && has_total) {
+    __syncwarp();
+    double canon = 0.0;
+    if (lane < kAcc6) canon = Canonical6Entry(lane, red.total, st.R);
+    __syncwarp();
+    if (lane < kAcc6) red.total[lane] = canon;
+  }
+  NLO_STAMP(10);
+  // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs (the pushing
+  // CTA stores into the slot of every rank, every CTA of every rank polls its local slots and
+  // adds them in rank order => bit-identical sums and steps everywhere), through the local slot
+  // when CTA 0 gathered on behalf of the grid.
+  if (p.use_peer || grid_exchange) {
+    const bool pusher = has_total;
+    // one exchange per loop iteration in every launch shape that exchanges
+    const unsigned long long seq = red.seq0 + static_cast<unsigned long long>(it) + 1ULL;
+    unsigned int xtag;
+    int nsrc;
+    const unsigned long long* src;
+    if (p.use_peer) {
+      xtag = static_cast<unsigned int>(seq);
+      const int xpar = static_cast<int>(seq & 1ULL);
+      nsrc = p.peer.nranks;
+      src = p.peer.slots[p.peer.rank] + static_cast<size_t>(xpar) * kMaxRanks * kPeerWords;
+      if (pusher && tid < NACC) {  // the thread that holds red.total[tid]
+        const size_t slot = (static_cast<size_t>(xpar) * kMaxRanks + p.peer.rank) * kPeerWords + 2 * tid;
+        for (int r = 0; r < nsrc; ++r) StoreLL(p.peer.slots[r] + slot, red.total[tid], xtag);
+      }
+    } else {
+      xtag = p.tag_base + static_cast<unsigned int>(it) + 1u;
+      nsrc = 1;
+      unsigned long long* slot = p.ll_sums + (static_cast<size_t>(problem) * 2 + (it & 1)) * kPeerWords;
+      src = slot;
+      if (pusher && tid < NACC) StoreLL(slot + 2 * tid, red.total[tid], xtag);
+    }
+    __syncthreads();  // gather_lanes is reused
+    GatherLL<NACC>(src, kPeerWords, nsrc, xtag, p.use_peer ? kPeerTimeoutNs : kGridTimeoutNs,
+                   red.gather_lanes, red.total, &red.fail);
+    if (tid == 0) {
+      red.exchanges += 1;
+      if (p.use_peer && red.fail && pusher) *p.peer.error = 1;
+    }
+  }
+  if (red.fail) return kReduceFailed;
+  if (p.mode == kModeAssemble) {
+    if (warp == 0) {
+      __syncwarp();
+      if (lane < NACC && writer) p.sums[problem * 32 + lane] = red.total[lane];
+    }
+    return kReduceAssembled;
+  }
+  return kReduceStep;
+}
+
+// The damped step of one iteration on the canonical sums in red.total: warp 0 of the CTA, lane 0
+// computing (the 6x6 factorisation is one dependent chain), all lanes copying the new state out.
+template <int KIND>
+__device__ __forceinline__ void StepPhase(ReduceArea& red, const IterParams& p, State* st_global, int it) {
+  NLO_STAMP(12);
+  const int lane = threadIdx.x & 31;
+  const bool writer = (blockIdx.x == 0) || !p.persistent;
+  State& st = red.state;
+  __syncwarp();
+  if (lane == 0) {
+    double* trace_row = nullptr;
+    if (p.trace != nullptr && writer)
+      trace_row = p.trace + (static_cast<size_t>(blockIdx.y) * p.max_iterations + st.iteration) * KindTraits<KIND>::kTrace;
+    if (KIND == kNdt3)
+      Step3(red.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations, trace_row);
+    else
+      Step6(red.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations, trace_row);
+  }
+  NLO_STAMP(13);
+  __syncwarp();
+  if (writer) {  // the state in HBM: what the host reads, and what the next launch starts from
+    constexpr int kWords = static_cast<int>(sizeof(State) / sizeof(double));
+    if (lane < kWords) reinterpret_cast<double*>(st_global)[lane] = reinterpret_cast<const double*>(&st)[lane];
+  }
+  NLO_STAMP(14);
+}
+
+// Reduction, exchange and step of iteration `it`, called by all threads of the CTA after the tile
+// loop; returns a ReduceOutcome.
+template <int KIND>
+__device__ __forceinline__ int PostTileBody(ReduceArea& red, const IterParams& p, State* st_global, int it) {
+  const int outcome = ReduceAndExchange<KIND>(red, p, it);
+  NLO_STAMP(11);
+  if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(red, p, st_global, it);
+  return outcome;
+}
+// The streaming kernel's tile loop uses all 128 registers of its 2-CTAs-per-SM budget, and ptxas
+// budgets a directly called (or inlined) function together with its caller, which pushes dozens of
+// spills into the tile loop.  It therefore calls this non-inlined copy through a pointer the
+// compiler cannot see through: a plain ABI call, the callee saves what it uses, the tile loop keeps
+// its registers.  The price (~1 us per iteration: call, register saves, generic addressing) only
+// matters for latency-bound registrations, which run the resident kernel below instead.
+template <int KIND>
+__device__ __noinline__ int PostTilePhase(ReduceArea& red, const IterParams& p, State* st_global, int it) {
+  return PostTileBody<KIND>(red, p, st_global, it);
+}
+
+template <int KIND>
+__device__ __noinline__ void StepOnlyPhase(ReduceArea& red, const IterParams& p, State* st_global, int it) {
+  StepPhase<KIND>(red, p, st_global, it);
 }
 
 template <int KIND, int LOSS, typename ST>
-__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
+__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const __grid_constant__ IterParams p) {
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = PlanesOf<KIND, ST>();
@@ -217,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   const int problem = blockIdx.y;
   const int grid_x = gridDim.x;
   State* st_global = p.states + problem;
-  State& st = sm.state;  // CTA-local copy; in the persistent path every CTA steps it redundantly
+  State& st = sm.red.state;  // CTA-local copy; in the persistent path every CTA steps it redundantly
 
   if (tid == 0) {
     if (p.mode != kModeStepOnly) {
@@ -228,6 +512,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       FenceBarrierInit();
     }
     st = *st_global;
+    sm.red.fail = 0;
+    // sequence number of the peer exchange buffers (monotonic across launches) and exchanges made;
+    // kept in shared memory: the tile loop has no register to spare
+    sm.red.seq0 = p.use_peer ? *p.peer.seq : 0ULL;
+    sm.red.exchanges = 0;
   }
   __syncthreads();
 
@@ -239,14 +528,6 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   const int my_tiles =
       (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
   const bool writer = (blockIdx.x == 0) || !p.persistent;  // who publishes state / trace / sums
-
-  // profiling aid (NLO_DEBUG_TIMES=1): CTA 0 / thread 0 stamps the phases of each iteration
-#define NLO_STAMP(slot)                                                                  \
-  do {                                                                                   \
-    if (p.debug_times != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 &&    \
-        it < kDebugIterations)                                                           \
-      p.debug_times[static_cast<size_t>(it) * 8 + (slot)] = GlobalTimerNs();             \
-  } while (0)
 
   const uint64_t policy_keep = PolicyEvictLast(), policy_stream = PolicyEvictFirst();
   // Ring positions are carried incrementally (no divisions in the tile loop): the consumers'
@@ -355,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
               }
             }
           }
-          if (lane < NACC) sm.warp_sums[warp][lane] = v[0];
+          if (lane < NACC) sm.red.warp_sums[warp][lane] = v[0];
         }
         if (!resident) {
           if (it + 1 < p.iterations_in_kernel && p.mode == kModeSolve) {
@@ -369,175 +650,40 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       NLO_STAMP(1);
       __syncthreads();
       NLO_STAMP(2);
-
-      // CTA sum over the 8 consumer warps, fixed order
-      if (tid < NACC) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += sm.warp_sums[w][tid];
-        sm.total[tid] = s;
-      }
-      if (grid_x > 1) {
-        // per-CTA partial -> HBM/L2; double-buffered by iteration parity for the persistent path
-        double* partial_base =
-            p.partials + static_cast<size_t>((it & 1) * gridDim.y + problem) * grid_x * NACC;
-        if (tid < NACC) {
-          __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, sm.total[tid]);
-          // persistent path: thread 0's releasing fence after the bar.sync below covers these
-          // stores by cumulativity; the ticket path fences per writer
-          if (!p.persistent) __threadfence();
-        }
-        if (p.persistent) {
-          // Persistent grid: every CTA arrives on a counter; CTA 0 (the leader) waits for all
-          // partials, reduces them, [all-reduces over NVLink], steps and PUBLISHES the new 160-byte
-          // state as 40 "LL" words (32 payload bits + the iteration number in one 8-byte store, so
-          // a word is valid the moment its number matches: no fence, no separate flag); the other
-          // CTAs poll those words -- one L2 round trip after the leader's stores -- and rebuild
-          // the state.
-          constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
-          unsigned int* counter = reinterpret_cast<unsigned int*>(p.sync_words + problem * kSyncStride);
-          unsigned long long* ll_state = p.sync_words + problem * kSyncStride + 8;
-          const unsigned int want = static_cast<unsigned int>(it) + 1u;
-          __syncthreads();
-          if (tid == 0) {
-            __threadfence();  // releases this CTA's partial (cumulative over the bar.sync above)
-            atomicAdd(counter, 1u);
-            sm.flag = 1;
-          }
-          const unsigned long long start = GlobalTimerNs();
-          if (blockIdx.x == 0) {
-            if (tid == 0) {
-              while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
-                if (GlobalTimerNs() - start > kGridTimeoutNs) { sm.flag = 0; break; }
-              __threadfence();
-            }
-            __syncthreads();
-            if (sm.flag == 0) {  // a CTA went missing (cannot happen under a cooperative launch)
-              if (tid == 0) { st.status = 2; st.done = 1; *st_global = st; }
-              __syncthreads();
-              if (tid < kStateWords) {  // still publish, so that the other CTAs leave as well
-                const unsigned long long bits = static_cast<unsigned long long>(
-                    __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
-                __stcg(ll_state + tid, (static_cast<unsigned long long>(want) << 32) |
-                                           ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
-              }
-              break;
-            }
-          } else {
-            __syncthreads();  // sm.flag = 1 visible
-            if (tid < kStateWords) {
-              const volatile unsigned long long* src = ll_state + tid;
-              unsigned long long w = *src;
-              while (static_cast<unsigned int>(w >> 32) != want) {
-                if (GlobalTimerNs() - start > kGridTimeoutNs) { sm.flag = 0; break; }
-                w = *src;
-              }
-              sm.halves[tid] = static_cast<unsigned int>(w);
-            }
-            __syncthreads();
-            if (sm.flag == 0) {  // the leader went missing
-              if (tid == 0) { st.status = 2; st.done = 1; }
-              __syncthreads();
-              break;
-            }
-            if (tid < kStateWords / 2)
-              reinterpret_cast<double*>(&st)[tid] = __longlong_as_double(static_cast<long long>(
-                  (static_cast<unsigned long long>(sm.halves[2 * tid + 1]) << 32) | sm.halves[2 * tid]));
-            __syncthreads();
-            continue;
-          }
-        } else {
-          __syncthreads();
-          if (tid == 0) {
-            const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
-            sm.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
-            if (sm.flag) p.tickets[problem] = 0u;  // ready for the next launch
-          }
-          __syncthreads();
-          if (sm.flag == 0) return;  // only the last CTA to arrive carries on
-          __threadfence();
-        }
-        NLO_STAMP(3);
-        // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
-        const int j = tid >> 3, l8 = tid & 7;
-        if (j < NACC) {
-          const double* base = partial_base + j;
-          double s = 0.0;
-          int g = l8;
-          // loads are issued 16 at a time (independent addresses, the tail predicated so that it
-          // costs one round trip instead of one per element); the adds keep the fixed order
-          for (; g < grid_x; g += 128) {
-            double v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int c = g + 8 * u;
-              v[u] = c < grid_x ? __ldcg(base + static_cast<size_t>(c) * NACC) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) s += v[u];
-          }
-          sm.warp_sums[l8][j] = s;
+      int (*volatile post_fn)(ReduceArea&, const IterParams&, State*, int) = &PostTilePhase<KIND>;
+      const int outcome = post_fn(sm.red, p, st_global, it);
+      if (outcome == kReduceLeave) return;
+      if (outcome == kReduceFailed) {  // a wait expired (GPU shared or preempted, a rank died): leave, do not hang
+        if (tid == 0) {
+          st.status = 2;
+          st.done = 1;
+          if (writer) *st_global = st;
         }
         __syncthreads();
-        if (tid < NACC) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) s += sm.warp_sums[w][tid];
-          sm.total[tid] = s;
-        }
+        break;
       }
-      __syncthreads();
-
-      NLO_STAMP(4);
-      // raw -> canonical (needs the R the sums were taken at)
-      if (KIND != kNdt3) {
-        double canon = 0.0;
-        if (tid < kAcc6) canon = Canonical6Entry(tid, sm.total, st.R);
-        __syncthreads();
-        if (tid < kAcc6) sm.total[tid] = canon;
-      }
-      __syncthreads();
-      if (p.use_peer) PeerAllReduce(p.peer, sm.total, NACC);
-      if (p.mode == kModeAssemble) {
-        if (tid < NACC && writer) p.sums[problem * 32 + tid] = sm.total[tid];
-        return;
-      }
+      if (outcome == kReduceAssembled) break;
     } else {
-      if (tid < NACC) sm.total[tid] = p.sums[problem * 32 + tid];
-      __syncthreads();
-    }
-
-    // ---------------- damped step by warp 0 (redundantly per CTA in the persistent path)
-    if (warp == 0) {
-      double* trace_row = nullptr;
-      if (p.trace != nullptr && writer)
-        trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st.iteration) *
-                                  T::kTrace;
-      if (lane == 0) {
-        if (KIND == kNdt3)
-          Step3(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
-                trace_row);
-        else
-          Step6(sm.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
-                trace_row);
+      if (tid < NACC) sm.red.total[tid] = p.sums[problem * 32 + tid];
+      if (warp == 0) {
+        void (*volatile step_fn)(ReduceArea&, const IterParams&, State*, int) = &StepOnlyPhase<KIND>;
+        step_fn(sm.red, p, st_global, it);
       }
-      if (lane == 0 && writer) *st_global = st;
     }
     NLO_STAMP(5);
     __syncthreads();
-    if (p.persistent && grid_x > 1 && p.mode == kModeSolve) {  // leader: publish the new state
-      constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
-      if (tid < kStateWords) {
-        const unsigned long long bits = static_cast<unsigned long long>(
-            __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
-        __stcg(p.sync_words + problem * kSyncStride + 8 + tid,
-               (static_cast<unsigned long long>(it + 1) << 32) |
-                   ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
-      }
-    }
     NLO_STAMP(6);
+    if (p.debug_all_ctas && it == 0 && tid == 0 && blockIdx.y == 0 && blockIdx.x < kDebugCtas && p.debug_times != nullptr) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.debug_times[(static_cast<size_t>(blockIdx.x) * kDebugIterations) * kDebugSlots + 7] = smid;
+    }
   }
-#undef NLO_STAMP
+  if (p.use_peer && tid == 0 && sm.red.exchanges > 0) {
+    const bool grid_exchange = p.persistent && grid_x > 1 && !p.gather_direct;
+    if (!grid_exchange || blockIdx.x == 0)
+      *p.peer.seq = sm.red.seq0 + static_cast<unsigned long long>(sm.red.exchanges);
+  }
   // a prefetch may still be in flight when the loop ends early: let it land before the CTA exits
   if (prefetched > 0) {
     for (int m = 0; m < prefetched; ++m) {
@@ -547,52 +693,334 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   }
 }
 
-// ------------------------------------------------------------------ dispatch
-template <int KIND, int LOSS, typename ST>
-static cudaError_t LaunchTyped(const IterParams& p, int grid_x, int num_problems,
-                               cudaStream_t stream) {
-  dim3 grid(grid_x, num_problems);
-  if (p.persistent) {
-    IterParams copy = p;
-    void* args[] = {&copy};
-    return cudaLaunchCooperativeKernel(
-        reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, ST>), grid, dim3(kThreads),
-        args, SmemBytes<KIND, ST>(), stream);
-  }
-  gn_iteration_kernel<KIND, LOSS, ST><<<grid, kThreads, SmemBytes<KIND, ST>(), stream>>>(p);
-  return cudaGetLastError();
-}
+// ------------------------------------------------------------------ resident kernel
+// gn_resident_kernel<KIND, LOSS>: the device-resident loop of a registration whose correspondences
+// fit the shared memory of the grid (<= resident_stages tiles per CTA: 100 k NDT points are 3 tiles
+// on each of 132 - 148 CTAs).  This is the latency-bound regime -- the reference's own problem
+// sizes, 9 k - 100 k correspondences -- where an iteration is a few microseconds and everything
+// that is not arithmetic shows: the kernel is therefore its own, small piece of code (it stays in
+// the instruction cache; the streaming kernel's per-iteration path does not), runs one CTA per SM
+// with up to 255 registers per thread so that the reduction, the exchange and the 6x6 step are
+// inlined next to the tile loop without spilling, reads the tiles from HBM exactly once per Solve
+// (one bulk copy per tile, one mbarrier) and takes two correspondences per thread and step for
+// instruction-level parallelism on the fp64 pipe.
+struct ResidentSmem {
+  ReduceArea red;
+  uint64_t full;  // all tiles of this CTA have landed
+};
 
 template <int KIND, int LOSS>
-static cudaError_t LaunchOne(const IterParams& p, int grid_x, int num_problems,
-                             cudaStream_t stream) {
-  if (p.f32) {
-    if (KIND == kReproj) return cudaErrorInvalidValue;  // fp32 storage exists for the NDT kinds only
-    return LaunchTyped<(KIND == kReproj ? kNdt6 : KIND), LOSS, float>(p, grid_x, num_problems, stream);
+__global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_constant__ IterParams p) {
+  using T = KindTraits<KIND>;
+  constexpr int NACC = T::kAcc;
+  constexpr int NPLANES = PlanesOf<KIND, double>();
+  constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(double);
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ResidentSmem& sm = *reinterpret_cast<ResidentSmem*>(smem_raw);
+  // stages start at the next 128-byte boundary after the header
+  double(*stages)[NPLANES][kTile] = reinterpret_cast<double(*)[NPLANES][kTile]>(
+      smem_raw + ((sizeof(ResidentSmem) + 127) / 128) * 128);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int problem = blockIdx.y;
+  const int grid_x = gridDim.x;
+  State* st_global = p.states + problem;
+  State& st = sm.red.state;
+  const bool writer = blockIdx.x == 0;
+
+  const Range range = p.ranges[problem];
+  const int64_t tile_lo = range.begin / kTile;
+  const int64_t span = (range.end + kTile - 1) / kTile - tile_lo;
+  const int my_tiles =
+      (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
+
+  if (tid == 0) {
+    MbarInit(&sm.full, 1);
+    FenceBarrierInit();
+    st = *st_global;
+    sm.red.fail = 0;
+    sm.red.seq0 = p.use_peer ? *p.peer.seq : 0ULL;
+    sm.red.exchanges = 0;
+    if (my_tiles > 0) {
+      MbarExpectTx(&sm.full, kStageBytes * static_cast<uint32_t>(my_tiles));
+      for (int m = 0; m < my_tiles; ++m) {
+        const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
+        BulkLoad(&stages[m][0][0], p.planes[0] + tile * (NPLANES * kTile), kStageBytes, &sm.full);
+      }
+    }
   }
-  return LaunchTyped<KIND, LOSS, double>(p, grid_x, num_problems, stream);
+  __syncthreads();
+  if (my_tiles > 0) MbarWait(&sm.full, 0);
+
+  // validity of this thread's correspondence in each tile (only the range's first / last tile are ragged)
+  auto valid_in = [&](int m) {
+    const int64_t idx = (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
+    return idx >= range.begin && idx < range.end;
+  };
+  auto one_point = [&](const double* v, const double* R, const double* t, bool valid, double* acc) {
+    if (KIND == kNdt6)
+      Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+    else if (KIND == kNdt3)
+      Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+    else
+      ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
+  };
+
+  for (int it = 0; it < p.iterations_in_kernel; ++it) {
+    if (st.done) break;  // uniform: every CTA steps the same state
+    NLO_STAMP(0);
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    double R[9], t[3];
+    if (KIND == kNdt3) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) R[k] = st.R[k];
+      t[0] = st.t[0];
+      t[1] = st.t[1];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = st.R[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = st.t[k];
+    }
+    int m = 0;
+    for (; m + 1 < my_tiles; m += 2) {  // two independent correspondences in flight per thread
+      double va[NPLANES], vb[NPLANES];
+#pragma unroll
+      for (int pl = 0; pl < NPLANES; ++pl) {
+        va[pl] = stages[m][pl][tid];
+        vb[pl] = stages[m + 1][pl][tid];
+      }
+      double accb[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) accb[k] = 0.0;
+      one_point(va, R, t, valid_in(m), acc);
+      one_point(vb, R, t, valid_in(m + 1), accb);
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] += accb[k];
+    }
+    if (m < my_tiles) {
+      double va[NPLANES];
+#pragma unroll
+      for (int pl = 0; pl < NPLANES; ++pl) va[pl] = stages[m][pl][tid];
+      one_point(va, R, t, valid_in(m), acc);
+    }
+    // warp reduction by recursive halving (see the streaming kernel): lane l ends with value l
+    {
+      double v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = (k < NACC) ? acc[k] : 0.0;
+#pragma unroll
+      for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          if (i < NACC) {
+            const double send = upper ? v[i] : v[i + half];
+            const double keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+          }
+        }
+      }
+      if (lane < NACC) sm.red.warp_sums[warp][lane] = v[0];
+    }
+    NLO_STAMP(1);
+    __syncthreads();
+    NLO_STAMP(2);
+    const int outcome = PostTileBody<KIND>(sm.red, p, st_global, it);
+    if (outcome == kReduceFailed) {
+      if (tid == 0) {
+        st.status = 2;
+        st.done = 1;
+        if (writer) *st_global = st;
+      }
+      __syncthreads();
+      break;
+    }
+    NLO_STAMP(5);
+    __syncthreads();
+    NLO_STAMP(6);
+    if (p.debug_all_ctas && it == 0 && tid == 0 && blockIdx.y == 0 && blockIdx.x < kDebugCtas && p.debug_times != nullptr) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.debug_times[(static_cast<size_t>(blockIdx.x) * kDebugIterations) * kDebugSlots + 7] = smid;
+    }
+  }
+  if (p.use_peer && tid == 0 && sm.red.exchanges > 0) {
+    const bool grid_exchange = grid_x > 1 && !p.gather_direct;
+    if (!grid_exchange || blockIdx.x == 0)
+      *p.peer.seq = sm.red.seq0 + static_cast<unsigned long long>(sm.red.exchanges);
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+struct KernelEntry {
+  const void* fn = nullptr;
+  size_t smem = 0;
+};
+
+template <int KIND, int LOSS>
+static KernelEntry EntryOne(bool f32) {
+  KernelEntry e;
+  if (f32) {
+    if (KIND == kReproj) return e;  // fp32 storage exists for the NDT kinds only
+    constexpr int K = (KIND == kReproj ? kNdt6 : KIND);
+    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<K, LOSS, float>);
+    e.smem = SmemBytes<K, float>();
+  } else {
+    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, double>);
+    e.smem = SmemBytes<KIND, double>();
+  }
+  return e;
 }
 
 template <int KIND>
-static cudaError_t LaunchKind(int loss, const IterParams& p, int grid_x, int num_problems,
-                              cudaStream_t stream) {
+static KernelEntry EntryKind(int loss, bool f32) {
   switch (loss) {
-    case kLossNone: return LaunchOne<KIND, kLossNone>(p, grid_x, num_problems, stream);
-    case kLossExponential: return LaunchOne<KIND, kLossExponential>(p, grid_x, num_problems, stream);
-    case kLossHuber: return LaunchOne<KIND, kLossHuber>(p, grid_x, num_problems, stream);
-    case kLossCauchy: return LaunchOne<KIND, kLossCauchy>(p, grid_x, num_problems, stream);
+    case kLossNone: return EntryOne<KIND, kLossNone>(f32);
+    case kLossExponential: return EntryOne<KIND, kLossExponential>(f32);
+    case kLossHuber: return EntryOne<KIND, kLossHuber>(f32);
+    case kLossCauchy: return EntryOne<KIND, kLossCauchy>(f32);
   }
-  return cudaErrorInvalidValue;
+  return KernelEntry();
+}
+
+static KernelEntry EntryFor(int kind, int loss, bool f32) {
+  switch (kind) {
+    case kNdt6: return EntryKind<kNdt6>(loss, f32);
+    case kNdt3: return EntryKind<kNdt3>(loss, f32);
+    case kReproj: return EntryKind<kReproj>(loss, f32);
+  }
+  return KernelEntry();
+}
+
+// Resident kernel (fp64 storage only): shared memory = header + one stage per tile of the CTA.
+constexpr size_t kResidentHeaderBytes = ((sizeof(ResidentSmem) + 127) / 128) * 128;
+constexpr size_t kMaxDynamicSmem = 227 * 1024;
+
+static size_t ResidentStageBytes(int kind) {
+  return static_cast<size_t>(kind == kReproj ? kReprojPlanes : kNdtPlanes) * kTile * sizeof(double);
+}
+
+template <int KIND>
+static const void* ResidentKind(int loss) {
+  switch (loss) {
+    case kLossNone: return reinterpret_cast<const void*>(&gn_resident_kernel<KIND, kLossNone>);
+    case kLossExponential: return reinterpret_cast<const void*>(&gn_resident_kernel<KIND, kLossExponential>);
+    case kLossHuber: return reinterpret_cast<const void*>(&gn_resident_kernel<KIND, kLossHuber>);
+    case kLossCauchy: return reinterpret_cast<const void*>(&gn_resident_kernel<KIND, kLossCauchy>);
+  }
+  return nullptr;
+}
+
+static const void* ResidentFor(int kind, int loss) {
+  switch (kind) {
+    case kNdt6: return ResidentKind<kNdt6>(loss);
+    case kNdt3: return ResidentKind<kNdt3>(loss);
+    case kReproj: return ResidentKind<kReproj>(loss);
+  }
+  return nullptr;
+}
+
+int ResidentMaxStages(int kind) {
+  return static_cast<int>((kMaxDynamicSmem - kResidentHeaderBytes) / ResidentStageBytes(kind));
+}
+
+// Attributes of a launch: a persistent grid is launched cooperatively (all CTAs co-resident, the
+// kernel spins on words written by other CTAs), a cluster size > 1 adds the cluster dimension.
+static int FillAttributes(cudaLaunchAttribute* attrs, bool cooperative, int cluster) {
+  int n = 0;
+  if (cooperative) {
+    attrs[n].id = cudaLaunchAttributeCooperative;
+    attrs[n].val.cooperative = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = static_cast<unsigned int>(cluster);
+    attrs[n].val.clusterDim.y = 1;
+    attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  return n;
 }
 
 cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
-                            cudaStream_t stream) {
-  switch (kind) {
-    case kNdt6: return LaunchKind<kNdt6>(loss, p, grid_x, num_problems, stream);
-    case kNdt3: return LaunchKind<kNdt3>(loss, p, grid_x, num_problems, stream);
-    case kReproj: return LaunchKind<kReproj>(loss, p, grid_x, num_problems, stream);
+                            int cluster, cudaStream_t stream) {
+  const KernelEntry e = EntryFor(kind, loss, p.f32 != 0);
+  if (e.fn == nullptr || cluster < 1 || cluster > kMaxCluster || grid_x % cluster != 0) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid_x, num_problems);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = e.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  cfg.numAttrs = FillAttributes(attrs, p.persistent != 0, cluster);
+  cfg.attrs = attrs;
+  IterParams copy = p;
+  void* args[] = {&copy};
+  return cudaLaunchKernelExC(&cfg, e.fn, args);
+}
+
+cudaError_t LaunchResident(int kind, int loss, const IterParams& p, int grid_x, int num_problems, int cluster,
+                           int stages, cudaStream_t stream) {
+  const void* fn = ResidentFor(kind, loss);
+  if (fn == nullptr || p.f32 || cluster < 1 || cluster > kMaxCluster || grid_x % cluster != 0 || stages < 0 ||
+      stages > ResidentMaxStages(kind))
+    return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid_x, num_problems);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kResidentHeaderBytes + static_cast<size_t>(stages) * ResidentStageBytes(kind);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  cfg.numAttrs = FillAttributes(attrs, true, cluster);
+  cfg.attrs = attrs;
+  IterParams copy = p;
+  void* args[] = {&copy};
+  return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
+// CTAs of the iteration kernel (resident: of the resident kernel, one per SM) that can be
+// co-resident on the current device when launched in clusters of `cluster` CTAs (the GPCs do not
+// all hold a whole number of clusters).
+int MaxCoResidentCtas(int kind, int loss, bool f32, int cluster, bool resident) {
+  KernelEntry e = EntryFor(kind, loss, f32);
+  if (resident) {
+    e.fn = f32 ? nullptr : ResidentFor(kind, loss);
+    e.smem = kResidentHeaderBytes + static_cast<size_t>(ResidentMaxStages(kind)) * ResidentStageBytes(kind);
   }
-  return cudaErrorInvalidValue;
+  if (e.fn == nullptr) return 0;
+  if (cluster <= 1) {
+    int per_sm = 0, device = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, e.fn, kThreads, e.smem) != cudaSuccess ||
+        cudaGetDevice(&device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return per_sm * sms;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster * 64);  // any multiple of the cluster size
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = e.smem;
+  cudaLaunchAttribute attrs[2];
+  cfg.numAttrs = FillAttributes(attrs, false, cluster);
+  cfg.attrs = attrs;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, e.fn, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return clusters * cluster;
 }
 
 size_t IterationSmemBytes(int kind) {
@@ -603,29 +1031,23 @@ size_t IterationSmemBytes(int kind) {
   }
 }
 
-template <int KIND, int LOSS>
-static cudaError_t ConfigureOne() {
-  cudaError_t e = cudaFuncSetAttribute(gn_iteration_kernel<KIND, LOSS, double>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(SmemBytes<KIND, double>()));
-  if (e != cudaSuccess || KIND == kReproj) return e;
-  return cudaFuncSetAttribute(gn_iteration_kernel<(KIND == kReproj ? kNdt6 : KIND), LOSS, float>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(SmemBytes<(KIND == kReproj ? kNdt6 : KIND), float>()));
-}
-template <int KIND>
-static cudaError_t ConfigureKind() {
-  cudaError_t e;
-  if ((e = ConfigureOne<KIND, kLossNone>()) != cudaSuccess) return e;
-  if ((e = ConfigureOne<KIND, kLossExponential>()) != cudaSuccess) return e;
-  if ((e = ConfigureOne<KIND, kLossHuber>()) != cudaSuccess) return e;
-  return ConfigureOne<KIND, kLossCauchy>();
-}
 cudaError_t ConfigureKernels() {
-  cudaError_t e;
-  if ((e = ConfigureKind<kNdt6>()) != cudaSuccess) return e;
-  if ((e = ConfigureKind<kNdt3>()) != cudaSuccess) return e;
-  return ConfigureKind<kReproj>();
+  for (int kind = 0; kind < 3; ++kind)
+    for (int loss = 0; loss < 4; ++loss)
+      for (int f32 = 0; f32 < 2; ++f32) {
+        const KernelEntry e = EntryFor(kind, loss, f32 != 0);
+        if (e.fn == nullptr) continue;
+        const cudaError_t err = cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     static_cast<int>(e.smem));
+        if (err != cudaSuccess) return err;
+      }
+  for (int kind = 0; kind < 3; ++kind)
+    for (int loss = 0; loss < 4; ++loss) {
+      const cudaError_t err = cudaFuncSetAttribute(ResidentFor(kind, loss), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(kMaxDynamicSmem));
+      if (err != cudaSuccess) return err;
+    }
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------ state init / finish

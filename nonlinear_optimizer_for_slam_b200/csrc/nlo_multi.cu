@@ -185,6 +185,11 @@ int CreateContext(const int* devices, int n, nlo_context** out) {
     nlo_context* sub = ctx->subs[static_cast<size_t>(r)];
     sub->grid_single = std::max(1, sub->grid_single / m);
     sub->grid_small = std::max(1, sub->grid_small / m);
+    sub->device_share = m;
+    if (m > 1) {  // several cooperative cluster launches do not reliably co-schedule on one device
+      sub->cluster_small = 1;
+      sub->cluster_big = 1;
+    }
   }
   ctx->sm_count = ctx->subs[0]->sm_count;
   ctx->grid_single = ctx->subs[0]->grid_single;

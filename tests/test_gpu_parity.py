@@ -269,8 +269,10 @@ def test_large_generated_shards_sum_and_repeat(ctx, nlo, n):
     r1 = prob.solve6(pose, nlo.Options(max_iterations=5), trace=True)
     r2 = prob.solve6(pose, nlo.Options(max_iterations=5), trace=True)
     assert np.array_equal(r1["trace"], r2["trace"]) and np.array_equal(r1["pose"], r2["pose"])
-    # the first trace row is the assembly at the initial pose
-    np.testing.assert_array_equal(r1["trace"][0, :21], H)
+    # the first trace row is the assembly at the initial pose (the persistent loop pre-reduces the
+    # per-CTA sums inside thread-block clusters, the single assembly adds them flat: same numbers
+    # up to the order of a few hundred fp64 additions)
+    assert_sums_close(r1["trace"][0, :21], r1["trace"][0, 21:27], r1["trace"][0, 27], H, g, c, tol=1e-12)
     prob.close()
 
 
