@@ -332,3 +332,174 @@ def simd_reproj_assemble(planes, n, intrinsics, R, t, loss_kind=LOSS_NONE, loss_
                                           ctypes.c_int(num_threads), H.ctypes.data_as(_c_double_p),
                                           g.ctypes.data_as(_c_double_p), ctypes.byref(cost))
     return H, g, cost.value
+
+
+# ---------------------------------------------------------------------------------------------
+# Eigen's SelfAdjointEigenSolver<Matrix3d>::compute(), restated.
+#
+# The reference's NDT fixture stores sqrt_information = diag(eigval^-1/2) * V with V =
+# eigsol.eigenvectors() -- V, not V^T (tests/simple_optimization_test.cc:275-276,
+# tests/3dof_6dof_comparison_test.cc:246-247) -- so S^T S = V^T D^2 V depends on the SIGN of every
+# eigenvector column, which no convention fixes: it is whatever the solver's arithmetic leaves.
+# The published logs (results/maha_*.txt) can therefore only be reproduced with Eigen's own
+# algorithm.  Eigen is a third-party dependency that is absent from /root/reference (found by
+# find_package(Eigen3), CMakeLists.txt; 3.3.7 / 3.4.0 in the distributions of the time); this is
+# its published algorithm (Eigen/src/Eigenvalues/SelfAdjointEigenSolver.h, Tridiagonalization.h,
+# Eigen/src/Jacobi/Jacobi.h): scale to [-1, 1], the closed-form 3x3 Householder tridiagonalisation
+# on the lower triangle, implicit symmetric QR steps with Wilkinson shift and Givens rotations
+# accumulated on the right, selection sort into ascending eigenvalues.  `version` selects the
+# deflation test, the only difference between 3.3 and 3.4 that matters here.
+# ---------------------------------------------------------------------------------------------
+def _eigen_make_givens(p, q):
+    if q == 0.0:
+        return (-1.0 if p < 0.0 else 1.0), 0.0
+    if p == 0.0:
+        return 0.0, (1.0 if q < 0.0 else -1.0)
+    if abs(p) > abs(q):
+        t = q / p
+        u = np.sqrt(1.0 + t * t)
+        if p < 0.0:
+            u = -u
+        c = 1.0 / u
+        return c, -t * c
+    t = p / q
+    u = np.sqrt(1.0 + t * t)
+    if q < 0.0:
+        u = -u
+    s = -1.0 / u
+    return -t * s, s
+
+
+def eigen_selfadjoint3(A, version="3.4"):
+    """(eigenvalues ascending, eigenvectors as columns) of a symmetric 3x3, as Eigen computes them."""
+    A = np.array(A, dtype=np.float64)
+    m = np.tril(A)
+    scale = np.abs(m).max()
+    if scale == 0.0:
+        scale = 1.0
+    m = m / scale
+    diag = np.zeros(3)
+    sub = np.zeros(2)
+    tol = np.finfo(np.float64).tiny
+    diag[0] = m[0, 0]
+    v1norm2 = m[2, 0] * m[2, 0]
+    if v1norm2 <= tol:
+        diag[1], diag[2] = m[1, 1], m[2, 2]
+        sub[0], sub[1] = m[1, 0], m[2, 1]
+        Q = np.eye(3)
+    else:
+        beta = np.sqrt(m[1, 0] * m[1, 0] + v1norm2)
+        inv_beta = 1.0 / beta
+        m01 = m[1, 0] * inv_beta
+        m02 = m[2, 0] * inv_beta
+        q = 2.0 * m01 * m[2, 1] + m02 * (m[2, 2] - m[1, 1])
+        diag[1] = m[1, 1] + m02 * q
+        diag[2] = m[2, 2] - m02 * q
+        sub[0] = beta
+        sub[1] = m[2, 1] - m01 * q
+        Q = np.array([[1.0, 0.0, 0.0], [0.0, m01, m02], [0.0, m02, -m01]])
+    n = 3
+    end, start, it = n - 1, 0, 0
+    eps = np.finfo(np.float64).eps
+    while end > 0:
+        for i in range(start, end):
+            if version == "3.4":
+                if abs(sub[i]) < tol:
+                    sub[i] = 0.0
+                else:
+                    scaled = sub[i] / eps
+                    if scaled * scaled <= abs(diag[i]) + abs(diag[i + 1]):
+                        sub[i] = 0.0
+            else:  # 3.3: isMuchSmallerThan(|e|, |d_i| + |d_i+1|, 2 eps) || |e| <= min
+                if abs(sub[i]) <= (abs(diag[i]) + abs(diag[i + 1])) * 2.0 * eps or abs(sub[i]) <= tol:
+                    sub[i] = 0.0
+        while end > 0 and sub[end - 1] == 0.0:
+            end -= 1
+        if end <= 0:
+            break
+        it += 1
+        if it > 30 * n:
+            break
+        start = end - 1
+        while start > 0 and sub[start - 1] != 0.0:
+            start -= 1
+        # tridiagonal_qr_step
+        td = (diag[end - 1] - diag[end]) * 0.5
+        e = sub[end - 1]
+        mu = diag[end]
+        if td == 0.0:
+            mu -= abs(e)
+        elif e != 0.0:
+            e2 = e * e
+            h = np.hypot(td, e)
+            if e2 == 0.0:
+                mu -= e / ((td + (h if td > 0.0 else -h)) / e)
+            else:
+                mu -= e2 / (td + (h if td > 0.0 else -h))
+        x = diag[start] - mu
+        z = sub[start]
+        k = start
+        while k < end and z != 0.0:
+            c, s = _eigen_make_givens(x, z)
+            sdk = s * diag[k] + c * sub[k]
+            dkp1 = s * sub[k] + c * diag[k + 1]
+            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1])
+            diag[k + 1] = s * sdk + c * dkp1
+            sub[k] = c * sdk - s * dkp1
+            if k > start:
+                sub[k - 1] = c * sub[k - 1] - s * z
+            x = sub[k]
+            if k < end - 1:
+                z = -s * sub[k + 1]
+                sub[k + 1] = c * sub[k + 1]
+            # Q = Q * G: applyOnTheRight(k, k+1, rot) == rotation by rot.transpose() of the two columns
+            xk = Q[:, k].copy()
+            yk = Q[:, k + 1].copy()
+            Q[:, k] = c * xk - s * yk
+            Q[:, k + 1] = s * xk + c * yk
+            k += 1
+    # ascending selection sort, columns follow
+    for i in range(n - 1):
+        kmin = int(np.argmin(diag[i:]))
+        if kmin > 0:
+            diag[[i, i + kmin]] = diag[[i + kmin, i]]
+            Q[:, [i, i + kmin]] = Q[:, [i + kmin, i]]
+    return diag * scale, Q
+
+
+def reference_ndt_grid(points, voxel, version="3.4"):
+    """UpdateNdtMap of the reference's test mains (tests/simple_optimization_test.cc:236-280) on a
+    dense grid, literally: raw moments accumulated in point order starting from moment = Identity
+    (types.h:14), cov = moment / n - mean mean^T, Eigen's eigenvectors, S = diag(w^-1/2) * V.
+    Same dictionary as synthetic.build_ndt_grid."""
+    inv = 1.0 / voxel
+    key = np.floor(points * inv).astype(np.int64)
+    kmin = key.min(0)
+    dims = (key.max(0) - kmin + 1).astype(np.int64)
+    k = key - kmin
+    lin = (k[:, 2] * dims[1] + k[:, 1]) * dims[0] + k[:, 0]
+    cells = int(dims.prod())
+    count = np.bincount(lin, minlength=cells)
+    s = np.stack([np.bincount(lin, weights=points[:, a], minlength=cells) for a in range(3)], 1)
+    moment = np.zeros((cells, 3, 3))
+    for a in range(3):
+        for b in range(3):
+            moment[:, a, b] = np.bincount(lin, weights=points[:, a] * points[:, b], minlength=cells)
+    mean = np.zeros((cells, 3))
+    S = np.zeros((cells, 3, 3))
+    valid = np.zeros(cells, dtype=np.uint8)
+    for c in range(cells):
+        if count[c] < 5:
+            continue
+        mu = s[c] / count[c]
+        cov = (moment[c] + np.eye(3)) / count[c] - np.outer(mu, mu)
+        w, V = eigen_selfadjoint3(cov, version)
+        if w[2] < 0.01:
+            continue
+        w[0] = max(w[0], w[2] * 0.01)
+        w[1] = max(w[1], w[2] * 0.01)
+        mean[c] = mu
+        S[c] = np.diag(1.0 / np.sqrt(w)) @ V
+        valid[c] = 1
+    return {"origin": kmin.astype(np.float64) * voxel, "dims": dims.astype(np.int32), "voxel": float(voxel),
+            "mean": mean, "sqrt_info": np.ascontiguousarray(S.reshape(cells, 9)), "valid": valid}

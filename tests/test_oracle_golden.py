@@ -290,3 +290,125 @@ def test_ndt_fixture_cost_band(oracle):
         assert abs(got - ref) / ref < 0.02, (costs, iters)
     R, t = oracle.pose_to_Rt(pose)
     np.testing.assert_allclose(t, [-0.196416, 0.121469, 0.304836], atol=5e-3)  # :24
+
+
+def _fixture_loop(oracle, grid, true_T, solve):
+    """OptimizePoseAnalytic* of the reference's test mains (simple_optimization_test.cc:473-505,
+    3dof_6dof_comparison_test.cc:382-413): <= 10 x {match <= 2 nearest means within 1 m, Solve}."""
+    from scipy.spatial import cKDTree
+    room = oracle.room_points()
+    k = np.floor(room * 10.0).astype(np.int64)
+    _, first = np.unique(k, axis=0, return_index=True)
+    filtered = room[np.sort(first)]
+    Tinv = np.linalg.inv(true_T)
+    local = filtered @ Tinv[:3, :3].T + Tinv[:3, 3]
+    vidx = np.nonzero(grid["valid"])[0]
+    tree = cKDTree(grid["mean"][vidx])
+    pose = _pose0(oracle)
+    costs, iters = [], []
+    for _ in range(10):
+        R, t = oracle.pose_to_Rt(pose)
+        d, idx = tree.query(local @ R.T + t, k=2, distance_upper_bound=1.0)
+        sel = np.isfinite(d)
+        pi = np.repeat(np.arange(len(local)), 2).reshape(-1, 2)[sel]
+        ci = vidx[idx[sel]]
+        last = pose.copy()
+        pose, it, cost, _ = solve(local[pi], grid["mean"][ci], grid["sqrt_info"][ci], pose, 1, [1.0, 1.0])
+        costs.append(cost); iters.append(it)
+        Ra, ta = oracle.pose_to_Rt(last); Rb, tb = oracle.pose_to_Rt(pose)
+        dq = oracle.rotmat_to_quat(Ra.T @ Rb)
+        if np.linalg.norm(ta - tb) < 1e-5 and np.linalg.norm(dq[:3]) < 1e-5:
+            break
+    return costs, iters, pose
+
+
+def test_eigen_solver_restatement(oracle):
+    """oracle.eigen_selfadjoint3 (Eigen's SelfAdjointEigenSolver<Matrix3d>::compute restated) is an
+    eigen-decomposition: A = V diag(w) V^T, V orthonormal, w ascending -- and on the fixture's map
+    44 of the 96 cells have a two-fold DEGENERATE eigenvalue (a fully covered 1 m x 1 m patch of
+    floor or wall: relative gap ~1e-13), i.e. an arbitrary basis of that eigenspace."""
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        B = rng.normal(size=(3, 3)); A = B @ B.T
+        w, V = oracle.eigen_selfadjoint3(A)
+        assert np.all(np.diff(w) >= 0)
+        np.testing.assert_allclose(V @ np.diag(w) @ V.T, A, atol=1e-12 * np.abs(A).max())
+        np.testing.assert_allclose(V.T @ V, np.eye(3), atol=1e-12)
+    grid = oracle.reference_ndt_grid(oracle.room_points(), 1.0)
+    assert int(grid["valid"].sum()) == 96
+    S = grid["sqrt_info"].reshape(-1, 3, 3)[grid["valid"] == 1]
+    d = np.linalg.norm(S, axis=2)  # |row k of diag(d) V| = d_k
+    degenerate = np.abs(d[:, 1] - d[:, 2]) / d[:, 2] < 1e-9
+    assert int(degenerate.sum()) == 44
+
+
+@pytest.mark.timeout(600)
+def test_ndt_fixture_logs_with_eigen_restated(oracle):
+    """The published NDT logs against the fixture built with Eigen's own eigen-solver algorithm
+    (oracle.reference_ndt_grid): sqrt_information = diag * V as the reference writes it.
+      results/maha_amd64_simple.txt:10-14   6-DoF  COST 17438.4/40, 17394.5/40, 17490.6/20, 17490.7/2
+      results/maha_3_vs_6_amd64.txt:18-23   6-DoF  COST 17857.8/40, 17526.6/40, 17494.8/30, 17490.7/9, DBL_MAX/0
+      results/maha_3_vs_6_amd64.txt:7-11    3-DoF  COST 17871.8/40, ...
+    Costs agree to 0.1 %, the iteration caps, the number of outer rounds and even the last line of
+    the second log (a Solve that starts converged: 0 iterations, cost DBL_MAX) are reproduced.  Not
+    to the digit: with S = diag * V, S^T S = V^T D^2 V depends on which basis the solver happens to
+    return for the degenerate eigenspace of 44 of the 96 cells (test above) -- rounding noise of
+    the reference's build (-O3 -march=native, FMA contraction), which no restatement can pin."""
+    grid = oracle.reference_ndt_grid(oracle.room_points(), 1.0)
+    costs, iters, pose = _fixture_loop(oracle, grid, syn.CFG1_TRUE, oracle.ndt6_solve)
+    assert iters[:2] == [40, 40] and len(iters) == 4 and abs(iters[2] - 20) <= 2 and iters[3] == 2
+    for got, ref in zip(costs, [17438.4, 17394.5, 17490.6, 17490.7]):
+        assert abs(got - ref) / ref < 1.5e-3, (costs, iters)
+    _, t = oracle.pose_to_Rt(pose)
+    np.testing.assert_allclose(t, [-0.196416, 0.121469, 0.304836], atol=2e-4)  # maha_amd64_simple.txt:24
+    T2 = syn.yaw_pose([-0.15, 0.05, 0.0], 0.2)  # 3dof_6dof_comparison_test.cc:77-80
+    costs, iters, pose = _fixture_loop(oracle, grid, T2, oracle.ndt6_solve)
+    assert iters[:2] == [40, 40] and len(iters) == 5 and iters[4] == 0 and costs[4] > 1e300
+    for got, ref in zip(costs[:4], [17857.8, 17526.6, 17494.8, 17490.7]):
+        assert abs(got - ref) / ref < 1.5e-3, (costs, iters)
+    R, t = oracle.pose_to_Rt(pose)
+    np.testing.assert_allclose(t, [-0.145667, 0.0484111, 0.00497979], atol=2e-4)  # :33
+    np.testing.assert_allclose(oracle.rotmat_to_quat(R), [-0.000218557, -0.001234, 0.099811, 0.995006], atol=1e-4)
+    costs3, iters3, _ = _fixture_loop(oracle, grid, T2, oracle.ndt3_solve)
+    assert iters3[0] == 40 and abs(costs3[0] - 17871.8) / 17871.8 < 1.5e-3  # :7
+
+
+@pytest.mark.timeout(900)
+def test_ndt3_fixture_cost_band(oracle):
+    """results/maha_3_vs_6_amd64.txt:7-11,31: the planar minimizer on the same fixture,
+    COST 17871.8/40, 17559.4/40, 17488.4/10, 17484.3/1, pose (-0.150014, 0.0478718), yaw 0.2000.
+    The planar path is the one that feels the arbitrary basis of the degenerate eigenspaces (the
+    6-DoF path can absorb the spurious y/z coupling in the three parameters the planar one lacks):
+    a fixed basis choice lands anywhere in a band -- the restated Eigen arithmetic at y = -0.043,
+    9 cm off.  So the pin is the band itself: over seeded random bases of the degenerate
+    eigenspaces the reference's numbers must lie inside the ensemble (they do: x = -0.15000 +- 2e-5
+    always, y in 0.045 .. 0.048, costs 17.8 - 18.0 k / 17.5 - 17.7 k / 17.5 - 17.6 k, iterations
+    40 / 25 - 40 / 6 - 9 / 1 - 2).  No sign convention reproduces the log; see DESIGN.md."""
+    base = oracle.reference_ndt_grid(oracle.room_points(), 1.0)
+    T2 = syn.yaw_pose([-0.15, 0.05, 0.0], 0.2)
+    S0 = base["sqrt_info"].reshape(-1, 3, 3)
+    rng = np.random.default_rng(1)
+    first, second, ys, xs, yaws = [], [], [], [], []
+    for _ in range(5):
+        S = S0.copy()
+        for c in np.nonzero(base["valid"])[0]:
+            d = np.linalg.norm(S[c], axis=1)
+            if abs(d[1] - d[2]) / d[2] < 1e-9:
+                V = S[c] / d[:, None]
+                a = rng.uniform(0.0, 2.0 * np.pi)
+                sgn = -1.0 if rng.random() < 0.5 else 1.0
+                v1 = np.cos(a) * V[:, 1] + np.sin(a) * V[:, 2]
+                v2 = sgn * (-np.sin(a) * V[:, 1] + np.cos(a) * V[:, 2])
+                V[:, 1], V[:, 2] = v1, v2
+                S[c] = d[:, None] * V
+        grid = dict(base, sqrt_info=np.ascontiguousarray(S.reshape(-1, 9)))
+        costs, iters, pose = _fixture_loop(oracle, grid, T2, oracle.ndt3_solve)
+        assert iters[0] == 40 and 3 <= len(iters) <= 5
+        R, t = oracle.pose_to_Rt(pose)
+        first.append(costs[0]); second.append(costs[1]); xs.append(t[0]); ys.append(t[1])
+        yaws.append(np.arctan2(R[1, 0], R[0, 0]))
+    assert min(first) - 150 < 17871.8 < max(first) + 150, first
+    assert min(second) - 80 < 17559.4 < max(second) + 80, second
+    assert np.max(np.abs(np.array(xs) + 0.150014)) < 1e-4
+    assert min(ys) - 2e-3 < 0.0478718 < max(ys) + 2e-3, ys
+    assert np.max(np.abs(np.array(yaws) - 0.2)) < 5e-4
