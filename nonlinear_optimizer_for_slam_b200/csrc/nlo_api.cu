@@ -139,7 +139,8 @@ GridPlan PlanPersistentGrid(nlo_context* ctx, const nlo_problem* pr, int kind, i
   GridPlan plan;
   const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(tiles, want));
   const int64_t tiles_per_cta = (tiles + ctas - 1) / ctas;
-  for (int cluster = small ? ctx->cluster_small : ctx->cluster_big; cluster >= 1; cluster >>= 1) {
+  (void)small;
+  for (int cluster = ctx->cluster_small; cluster >= 1; cluster >>= 1) {
     if (cluster > 1 && cluster > ctas) continue;  // no point in clusters of mostly idle CTAs
     const int cap = (CoResidentCtas(ctx, pr, kind, cluster, resident) / std::max(1, rows) / cluster) * cluster;
     if (cap < cluster) continue;
@@ -154,6 +155,9 @@ GridPlan PlanPersistentGrid(nlo_context* ctx, const nlo_problem* pr, int kind, i
     }
   }
   if (plan.gx < 1) plan.gx = 1;
+  if (ctx->d_debug_times != nullptr)
+    fprintf(stderr, "[nlo debug] plan: %lld tiles, want %d CTAs x %d rows -> %d CTAs in clusters of %d (%s kernel)\n",
+            static_cast<long long>(tiles), want, rows, plan.gx, plan.cluster, resident ? "resident" : "streaming");
   plan.direct = (plan.gx > 1 && plan.gx / plan.cluster <= ctx->direct_max_clusters) ? 1 : 0;
   return plan;
 }
@@ -187,21 +191,20 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
   const int comm = CommFor(ctx, pr);
   const int64_t tiles = (end_abs + kTile - 1) / kTile - begin_abs / kTile;
   const bool in_cta_loop = (comm == kCommNone) && (pr->batched || tiles <= kInCtaTiles);
-  const bool tags_fit = opt.max_iterations < 65535;  // the iteration number shares the 32-bit LL tag with the solve epoch
-  if (pr->batched && ctx->use_persistent && tags_fit && tiles > kInCtaTiles && 2 * num_problems <= ctx->grid_single) {
+  const bool tags_fit = opt.max_iterations < 65535;  // resident kernel: the iteration number shares the 32-bit LL tag with the solve epoch
+  if (pr->batched && ctx->use_persistent && tiles > kInCtaTiles && 2 * num_problems <= ctx->grid_single) {
     // A small batch: one CTA per registration would leave most SMs idle, so every registration
     // gets G = (2 x SMs) / B CTAs of ONE persistent cooperative grid (gridDim.y = registrations),
-    // each registration with its own clusters, partial slots and state.
-    const GridPlan plan = PlanPersistentGrid(ctx, pr, kind, tiles, num_problems, ctx->grid_single / num_problems, true);
-    if (plan.gx > 1) {
+    // each registration with its own leader CTA, arrival counter and published state.
+    const int gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ctx->grid_single / num_problems, tiles)));
+    {
       IterParams q = p;
       q.mode = kModeSolve;
       q.persistent = 1;
       q.iterations_in_kernel = opt.max_iterations;
-      q.gather_direct = plan.direct;
-      const int rc = NextEpoch(ctx, pr, &q.tag_base);
-      if (rc != NLO_OK) return rc;
-      const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, q, plan.gx, num_problems, plan.cluster, ctx->stream);
+      NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(num_problems) * kSyncStride * sizeof(unsigned long long),
+                                    ctx->stream));
+      const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, q, gx, num_problems, 1, ctx->stream);
       if (ce == cudaSuccess) return NLO_OK;
       if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
         return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
@@ -236,15 +239,15 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
       cudaGetLastError();  // not co-resident right now: the streaming kernel below
     }
   }
-  if (UsePersistent(ctx, pr) && tags_fit) {
+  if (UsePersistent(ctx, pr)) {
     // persistent cooperative grid: the whole loop in ONE launch.  An empty shard (a rank that owns
     // no points) still launches one CTA: it takes part in the all-reduce with zero sums.
-    const bool small = tiles < 4LL * ctx->grid_single;
-    const GridPlan plan = PlanPersistentGrid(ctx, pr, kind, tiles, 1, small ? ctx->grid_small : ctx->grid_single, small);
+    int gx = grid_x;
+    if (tiles < 4LL * ctx->grid_single)
+      gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, ctx->grid_small)));
     p.mode = kModeSolve;
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
-    p.gather_direct = (comm == kCommNone) ? plan.direct : 0;
     // Streaming a large scan runs fastest with 3 tiles in flight per CTA (measured on B200, fp64 NDT,
     // 64M points: depth 2 / 3 / 4 = 71.3 / 75.9 / 71.3 Gpoints/s); the batched one-CTA-per-registration
     // shape keeps all 4 allocated stages.
@@ -255,9 +258,8 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
       if (ctx->l2_keep_mb > 0.0 && scan_mb > ctx->l2_policy_min_mb && opt.max_iterations > 1)
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
     }
-    const int rc = NextEpoch(ctx, pr, &p.tag_base);
-    if (rc != NLO_OK) return rc;
-    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, plan.gx, 1, plan.cluster, ctx->stream);
+    NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, kSyncStride * sizeof(unsigned long long), ctx->stream));
+    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, 1, ctx->stream);
     if (ce == cudaSuccess) return NLO_OK;
     if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
       return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
@@ -266,7 +268,6 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     p.persistent = 0;
     p.iterations_in_kernel = 1;
     p.l2_keep_tiles = 0;
-    p.gather_direct = 0;
   }
   // One launch per iteration.  A batched problem only gets here when its cooperative launch was
   // refused; its registrations then run one CTA each (the partial buffer is sized for one grid row).
@@ -429,8 +430,27 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
   return NLO_OK;
 }
 
+// Grows the device trace buffer of a problem.  cudaMalloc / cudaFree may wait for the device to go
+// idle, so a multi-device context calls this for every shard BEFORE it starts the shards' solves:
+// on a device shared by several shards the kernels already running would spin on the one whose
+// host thread sits in cudaMalloc.
+int EnsureTrace(nlo_context* ctx, nlo_problem* pr, size_t need_doubles) {
+  if (need_doubles <= pr->trace_doubles) return NLO_OK;
+  NLO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (pr->d_trace) NLO_CUDA(ctx, cudaFree(pr->d_trace));
+  pr->d_trace = nullptr;
+  pr->trace_doubles = 0;
+  NLO_CUDA(ctx, cudaMalloc(&pr->d_trace, need_doubles * sizeof(double)));
+  pr->trace_doubles = need_doubles;
+  DropGraphs(pr);
+  return NLO_OK;
+}
+
 int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index, const double pose[16],
                  int64_t begin, int64_t end, double* H, int nh, double* g, int ng, double* cost) {
+  // (constructed first: whatever way this call returns, the other shards' threads are not left waiting)
+  RendezvousGuard rendezvous(
+      (ctx != nullptr && pr != nullptr && CommFor(ctx, pr) == kCommPeer) ? ctx->launch_barrier : nullptr, 2);
   if (ctx == nullptr || pr == nullptr || pose == nullptr || H == nullptr || g == nullptr || cost == nullptr)
     return Fail(ctx, NLO_EINVAL, "null argument");
   if ((kind == kReproj) != (pr->family == 1)) return Fail(ctx, NLO_EINVAL, "problem family mismatch");
@@ -456,7 +476,10 @@ int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index,
   p.sums = pr->d_sums + 32 * slot;
   p.mode = kModeAssemble;
   const int grid_x = GridFor(ctx, hr->begin, hr->end);
+  if (rendezvous.active()) NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  rendezvous.Sync();  // every shard is ready to launch
   NLO_CUDA(ctx, LaunchIteration(kind, ctx->loss_kind, p, grid_x, 1, 1, ctx->stream));
+  rendezvous.Sync();  // every shard's kernel is queued: only now may anything wait behind it
   if (comm == kCommNccl) {
     const int rc = NcclAllReduceSums(ctx, pr->d_sums + 32 * slot);
     if (rc != NLO_OK) return rc;
@@ -472,6 +495,8 @@ int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index,
 
 int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* options,
               double* poses, nlo_solve_result* results, double* trace, bool batched_call) {
+  RendezvousGuard rendezvous(
+      (ctx != nullptr && pr != nullptr && CommFor(ctx, pr) == kCommPeer) ? ctx->launch_barrier : nullptr, 2);
   if (ctx == nullptr || pr == nullptr || options == nullptr || poses == nullptr || results == nullptr)
     return Fail(ctx, NLO_EINVAL, "null argument");
   if ((kind == kReproj) != (pr->family == 1)) return Fail(ctx, NLO_EINVAL, "problem family mismatch");
@@ -484,13 +509,8 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
   const bool with_trace = (trace != nullptr) && !pr->batched && options->max_iterations > 0;
   if (with_trace) {
     const size_t need = static_cast<size_t>(options->max_iterations) * trace_width;
-    if (need > pr->trace_doubles) {
-      if (pr->d_trace) NLO_CUDA(ctx, cudaFree(pr->d_trace));
-      pr->d_trace = nullptr;
-      NLO_CUDA(ctx, cudaMalloc(&pr->d_trace, need * sizeof(double)));
-      pr->trace_doubles = need;
-      DropGraphs(pr);
-    }
+    const int rc = EnsureTrace(ctx, pr, need);
+    if (rc != NLO_OK) return rc;
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_trace, 0, need * sizeof(double), ctx->stream));
   }
   // ranges of the registrations (single problem: [0, n) resp. floor(n/4)*4 for the 3-DoF path,
@@ -521,8 +541,11 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
   NLO_CUDA(ctx, LaunchInitStates(pr->d_states, pr->d_poses, B, kind, ctx->stream));
   NLO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (options->max_iterations > 0) {
+    if (rendezvous.active()) NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rendezvous.Sync();  // every shard is ready to launch
     const int rc = RunLoop(ctx, pr, kind, *options, with_trace, B, begin_abs, end_abs);
     if (rc != NLO_OK) return rc;
+    rendezvous.Sync();  // every shard's loop is queued: only now may anything wait behind it
   }
   NLO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   NLO_CUDA(ctx, LaunchFinishStates(pr->d_states, pr->d_poses, pr->d_results, B, kind, ctx->stream));
@@ -649,7 +672,6 @@ int nlo_context_create(int device, nlo_context** out) {
   };
   auto pow2_floor = [](int v) { int p2 = 1; while (2 * p2 <= v) p2 *= 2; return p2; };
   ctx->cluster_small = pow2_floor(env_int("NLO_CLUSTER", 4, 1, kMaxCluster));
-  ctx->cluster_big = pow2_floor(env_int("NLO_CLUSTER_BIG", 2, 1, kMaxCluster));
   ctx->direct_max_clusters = env_int("NLO_DIRECT_MAX", 48, 0, 1 << 20);
   ctx->use_resident = env_int("NLO_NO_RESIDENT", 0, 0, 1) == 0;
   const char* tenv = getenv("NLO_INGEST_THREADS");

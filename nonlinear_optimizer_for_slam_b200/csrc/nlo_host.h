@@ -53,6 +53,64 @@ struct IngestRing {
   bool used[kSlots] = {false, false, false};
 };
 
+// Rendezvous of the host threads that drive the devices of a multi-device context.  Needed when one
+// device carries several shards (a test configuration: the device list names a device twice): the
+// shards' kernels spin on each other, so no host thread may queue work BEHIND its spinning kernel
+// (the read-back of the result, an event) before the kernels of all shards are in their queues --
+// work of different streams can share a hardware queue, and an entry that waits for a spinning
+// kernel then holds back the very kernel it spins for.
+class HostBarrier {
+ public:
+  explicit HostBarrier(int participants) : n_(participants) {}
+  void ArriveAndWait() {
+    std::unique_lock<std::mutex> lock(mu_);
+    const long generation = generation_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++generation_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lock, [&] { return generation_ != generation; });
+    }
+  }
+  void ArriveNoWait() {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (++count_ == n_) {
+      count_ = 0;
+      ++generation_;
+      cv_.notify_all();
+    }
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int n_;
+  int count_ = 0;
+  long generation_ = 0;
+};
+
+// The `phases` rendezvous points of one call; whatever is left when the call returns early is
+// arrived at without waiting, so the other threads never hang on a failed shard.
+class RendezvousGuard {
+ public:
+  RendezvousGuard(HostBarrier* barrier, int phases) : barrier_(barrier), left_(barrier ? phases : 0) {}
+  ~RendezvousGuard() {
+    while (left_-- > 0) barrier_->ArriveNoWait();
+  }
+  bool active() const { return left_ > 0; }
+  void Sync() {
+    if (left_ > 0) {
+      --left_;
+      barrier_->ArriveAndWait();
+    }
+  }
+
+ private:
+  HostBarrier* barrier_;
+  int left_;
+};
+
 // A persistent worker thread (one per device of a multi-device context).
 class Worker {
  public:
@@ -91,7 +149,6 @@ struct nlo_context {
   double l2_policy_min_mb = 0.0;  // only scans larger than this get an explicit policy
   int grid_small = 0;             // CTAs of the persistent path for L2-resident problems
   int cluster_small = 4;          // NLO_CLUSTER: CTAs per thread-block cluster, problems resident in smem / L2
-  int cluster_big = 2;            // NLO_CLUSTER_BIG: the same for streamed scans (must not strand SMs)
   int direct_max_clusters = 48;   // NLO_DIRECT_MAX: up to this many cluster partials every CTA gathers them itself
   bool use_resident = true;       // NLO_NO_RESIDENT=1: latency-bound registrations also run the streaming kernel
   int device_share = 1;           // sub-contexts of one multi-device context that sit on this device
@@ -120,6 +177,8 @@ struct nlo_context {
   // multi-device context (nlo_context_create_multi): this object is then only a dispatcher
   std::vector<nlo_context*> subs;
   std::vector<nlo::Worker*> workers;
+
+  nlo::HostBarrier* launch_barrier = nullptr;  // sub-context of a multi-device context that shares devices: see HostBarrier
 
   bool IsMulti() const { return !subs.empty(); }
   int EffectiveComm() const { return comm_suspended ? nlo::kCommNone : comm_kind; }
@@ -205,6 +264,7 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
                   nlo_problem** out, bool f32 = false);
 int AssembleImpl(nlo_context* ctx, nlo_problem* pr, int kind, int problem_index, const double pose[16],
                  int64_t begin, int64_t end, double* H, int nh, double* g, int ng, double* cost);
+int EnsureTrace(nlo_context* ctx, nlo_problem* pr, size_t need_doubles);
 int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* options, double* poses,
               nlo_solve_result* results, double* trace, bool batched_call);
 

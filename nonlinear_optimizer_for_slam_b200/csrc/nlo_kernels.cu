@@ -102,6 +102,25 @@ __device__ __forceinline__ unsigned long long GlobalTimerNs() {
   return t;
 }
 
+// Watchdog of a polled wait.  %globaltimer is slow to read (~100 ns, and every polling thread of
+// the GPU reading it at once makes it worse), so the spin loops count their polls and look at the
+// SM's cycle counter only every 1024th time; the limits are converted from ns at a nominal 2 GHz
+// (they are "never hang" limits of tens of seconds, the SM clock varying by 2x does not matter).
+struct SpinWatch {
+  unsigned int polls = 0;
+  long long start = 0;
+  // true when the wait has lasted longer than `limit_ns`
+  __device__ __forceinline__ bool Expired(unsigned long long limit_ns) {
+    if ((++polls & 1023u) != 0u) return false;
+    const long long now = clock64();
+    if (start == 0) {
+      start = now;
+      return false;
+    }
+    return static_cast<unsigned long long>(now - start) > 2ULL * limit_ns;
+  }
+};
+
 template <int KIND>
 struct KindTraits;
 template <>
@@ -132,6 +151,7 @@ struct ReduceArea {
   State state;                    // CTA-local copy of the registration state
   unsigned long long seq0;        // peer exchange sequence number at kernel start
   int exchanges;                  // peer exchanges made by this kernel (thread 0's bookkeeping)
+  unsigned int halves[kPeerWords];  // streaming kernel: payload halves of the published state (LL words)
   int flag;
   int fail;                       // a polled wait expired
 };
@@ -191,6 +211,12 @@ __device__ __forceinline__ void StoreClusterF64(double* local, unsigned int targ
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
 }
 
+__device__ __forceinline__ void StoreClusterU32(int* local, unsigned int target_rank, unsigned int v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(SmemAddr(local)), "r"(target_rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ "LL" words
 // A double travels as two 8-byte words, each = (tag << 32) | 32 payload bits, so that a word is
 // valid the moment its tag matches: one store, one (polled) load, no fence, no separate flag --
@@ -208,42 +234,41 @@ __device__ __forceinline__ void LoadLL(const unsigned long long* src, unsigned l
 }
 
 // Fixed-order sum of `n_src` LL records of NACC doubles (record c at base + c * stride_words):
-// thread (j, l8) polls value j of records l8, l8+8, ... -- up to 8 loads in flight per thread --
-// and adds them in record order, then the 8 lanes are added in lane order.  total[0..NACC) is
-// written by threads 0..NACC-1 (warp 0) after an internal __syncthreads; *fail is set when a
-// record did not show up within `timeout_ns`.  Called by all threads of the CTA.
+// thread (j, l8) polls value j of records l8, l8+8, ... -- two loads in flight -- and adds them in
+// record order, then the 8 lanes are added in lane order.  total[0..NACC) is written by threads
+// 0..NACC-1 (warp 0) after an internal __syncthreads; *fail is set when a record did not show up
+// within `timeout_ns`.  Called by all threads of the CTA.  Deliberately small and NOT inlined
+// (one copy): the per-iteration code of a latency-bound registration has to stay inside the 32 KB
+// instruction cache of the SM, a miss per 128-byte line of cold code costs more than the math.
 template <int NACC>
-__device__ __forceinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
-                                         unsigned int tag, unsigned long long timeout_ns,
-                                         double (*lanes)[kAcc6], double* total, int* fail) {
+__device__ __noinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
+                                      unsigned int tag, unsigned long long timeout_ns,
+                                      double (*lanes)[kAcc6], double* total, int* fail) {
   const int tid = threadIdx.x;
   const int j = tid >> 3, l8 = tid & 7;
   if (j < NACC) {
     double s = 0.0;
-    unsigned long long start = 0ULL;
-    for (int c0 = l8; c0 < n_src; c0 += 64) {
-      unsigned long long lo[8], hi[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = c0 + 8 * u;
-        if (c < n_src) LoadLL(base + static_cast<size_t>(c) * stride_words + 2 * j, lo[u], hi[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = c0 + 8 * u;
-        if (c < n_src) {
-          while (static_cast<unsigned int>(lo[u] >> 32) != tag || static_cast<unsigned int>(hi[u] >> 32) != tag) {
-            if (start == 0ULL) start = GlobalTimerNs();
-            if (GlobalTimerNs() - start > timeout_ns) {
-              *fail = 1;
-              lo[u] = hi[u] = static_cast<unsigned long long>(tag) << 32;
-              break;
-            }
-            LoadLL(base + static_cast<size_t>(c) * stride_words + 2 * j, lo[u], hi[u]);
-          }
-          s += __longlong_as_double(static_cast<long long>((hi[u] << 32) | (lo[u] & 0xffffffffULL)));
+    SpinWatch watch;
+    const unsigned long long* src = base + static_cast<size_t>(l8) * stride_words + 2 * j;
+    const size_t step = static_cast<size_t>(8) * stride_words;
+    unsigned long long lo, hi, nlo = 0ULL, nhi = 0ULL;
+    if (l8 < n_src) LoadLL(src, lo, hi);
+#pragma unroll 1
+    for (int c = l8; c < n_src; c += 8) {
+      const bool more = c + 8 < n_src;
+      if (more) LoadLL(src + step, nlo, nhi);  // the next record travels while this one is checked
+      while (static_cast<unsigned int>(lo >> 32) != tag || static_cast<unsigned int>(hi >> 32) != tag) {
+        if (watch.Expired(timeout_ns)) {
+          *fail = 1;
+          lo = hi = static_cast<unsigned long long>(tag) << 32;
+          break;
         }
+        LoadLL(src, lo, hi);
       }
+      s += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
+      src += step;
+      lo = nlo;
+      hi = nhi;
     }
     lanes[l8][j] = s;
   }
@@ -266,49 +291,50 @@ __device__ __forceinline__ void GatherLL(const unsigned long long* base, int str
   } while (0)
 
 enum ReduceOutcome : int {
-  kReduceStep = 0,     // red.total holds the canonical sums of the whole registration: step
-  kReduceLeave = 1,    // this CTA is done with the launch (not the last one of a one-iteration launch)
-  kReduceFailed = 2,   // a polled wait expired
-  kReduceAssembled = 3 // assemble mode: the sums were written out
+  kReduceStep = 0,    // red.total holds the canonical sums of the whole registration: step
+  kReduceFailed = 2   // a polled wait expired
 };
 
-// Everything between the tile loop and the damped step of iteration `it`: CTA sum, cluster
-// pre-reduction over distributed shared memory, LL-format cluster partials, their gather, the
-// rotation to the canonical frame and -- sharded across GPUs, or when CTA 0 gathers on behalf of
-// the grid -- the exchange of the canonical sums.
+// Everything between the tile loop and the damped step of iteration `it` in the resident kernel.
+//  1. CTA sum (fixed order over the 8 warps); the CTAs of a thread-block cluster hand their 28
+//     sums to the cluster's rank-0 CTA through distributed shared memory and meet at the hardware
+//     cluster barrier; rank 0 adds them in rank order and stores the cluster's partial as "LL"
+//     words (32 payload bits + the tag of this iteration per 8-byte store: a word is valid the
+//     moment its tag matches -- no counter, no fence).
+//  2. Only the rank-0 CTAs poll global memory.  gather_direct (few clusters): every rank-0 CTA
+//     gathers all cluster partials and adds them in cluster order.  Otherwise CTA 0 gathers,
+//     rotates to the canonical frame and stores the sums (LL again) into the local slot -- or,
+//     sharded across GPUs, into the slot of every rank over NVLink -- and the rank-0 CTAs gather
+//     those (in rank order: bit-identical sums, and therefore steps, on every GPU).
+//  3. Rank 0 hands the totals to the other CTAs of its cluster over distributed shared memory, second
+//     cluster barrier; the other CTAs sleep in that hardware barrier meanwhile instead of polling:
+//     132 CTAs polling the same few L2 lines serialise in the L2 slices and delay the very stores
+//     they wait for (measured: 2.7 us for the all-CTAs gather of 33 partials).
+//  4. Every CTA rotates to the canonical frame (if step 2 did not) and steps its own copy of the state.
 template <int KIND>
-__device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterParams& p, int it) {
+__device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterParams& p, const CanonPlan& plan, int it) {
   constexpr int NACC = KindTraits<KIND>::kAcc;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int problem = blockIdx.y;
   const int grid_x = gridDim.x;
-  const bool writer = (blockIdx.x == 0) || !p.persistent;
   State& st = red.state;
   NLO_STAMP(8);
 
-  // CTA sum over the 8 consumer warps, fixed order; thread k < NACC (warp 0) owns value k
   double cta_sum = 0.0;
   if (tid < NACC) {
 #pragma unroll
     for (int w = 0; w < kConsumerWarps; ++w) cta_sum += red.warp_sums[w][tid];
   }
+  // the cluster this CTA belongs to (1 x 1 x 1 when the launch carries no cluster attribute)
+  const unsigned int csize = ClusterSize(), crank = ClusterCtaRank();
+  const bool leader = crank == 0;
+  const bool grid_exchange = grid_x > 1 && !p.gather_direct;  // CTA 0 gathers on behalf of the grid
+  bool canonical_done = false;
   if (grid_x == 1) {
     if (tid < NACC) red.total[tid] = cta_sum;
     NLO_STAMP(3);
-  } else if (p.persistent) {
-    // Persistent grid.  No counter, no fence, no leader round trip:
-    //  1. the CTAs of a thread-block cluster hand their 28 sums to the cluster's rank-0 CTA through
-    //     distributed shared memory and meet at the hardware cluster barrier; rank 0 adds them in
-    //     rank order and stores the cluster's partial as "LL" words (32 payload bits + the tag of
-    //     this iteration per 8-byte store: a word is valid the moment its tag matches);
-    //  2. gather_direct (few clusters): EVERY CTA polls all cluster partials, adds them in cluster
-    //     order and performs the identical step on its own copy of the state -- one L2 round trip
-    //     between the last partial and the new pose everywhere.  Otherwise CTA 0 gathers, rotates
-    //     to the canonical frame and writes the sums (LL again) to the local slot -- or, sharded
-    //     across GPUs, into the slot of every rank over NVLink -- and every CTA polls those.
-    // The cluster this CTA belongs to is 1 x 1 x 1 when the launch carries no cluster attribute.
-    const unsigned int csize = ClusterSize(), crank = ClusterCtaRank();
+  } else {
     const int n_clusters = static_cast<int>(ClusterCountX()), cluster_id = static_cast<int>(ClusterIdX());
     const int parity = it & 1;
     const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;
@@ -317,79 +343,25 @@ __device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterPara
     if (csize > 1) {
       if (tid < NACC) StoreClusterF64(&red.cluster_part[parity][crank][tid], 0u, cta_sum);
       ClusterSync();
-      if (crank == 0 && tid < NACC) {
+      if (leader && tid < NACC) {
         cta_sum = 0.0;
         for (unsigned int r = 0; r < csize; ++r) cta_sum += red.cluster_part[parity][r][tid];
       }
     }
-    if (crank == 0 && tid < NACC)
+    if (leader && tid < NACC)
       StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag);
     NLO_STAMP(3);
-    if (p.gather_direct || blockIdx.x == 0)
+    if (grid_exchange ? blockIdx.x == 0 : leader)
       GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, kGridTimeoutNs, red.gather_lanes, red.total, &red.fail);
-  } else {
-    // one launch per iteration: per-CTA partial -> HBM/L2, the last CTA to arrive (ticket) sums
-    double* partial_base = p.partials + static_cast<size_t>(problem) * grid_x * NACC;
-    if (tid < NACC) {
-      __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, cta_sum);
-      __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
-      red.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
-      if (red.flag) p.tickets[problem] = 0u;  // ready for the next launch
-    }
-    __syncthreads();
-    if (red.flag == 0) return kReduceLeave;  // only the last CTA to arrive carries on
-    __threadfence();
-    NLO_STAMP(3);
-    // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
-    const int j = tid >> 3, l8 = tid & 7;
-    if (j < NACC) {
-      const double* base = partial_base + j;
-      double s = 0.0;
-      // loads are issued 16 at a time (independent addresses, the tail predicated so that it
-      // costs one round trip instead of one per element); the adds keep the fixed order
-      for (int g = l8; g < grid_x; g += 128) {
-        double v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int c = g + 8 * u;
-          v[u] = c < grid_x ? __ldcg(base + static_cast<size_t>(c) * NACC) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) s += v[u];
-      }
-      red.gather_lanes[l8][j] = s;
-    }
-    __syncthreads();
-    if (tid < NACC) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red.gather_lanes[w][tid];
-      red.total[tid] = s;
-    }
   }
   NLO_STAMP(4);
-  // raw -> canonical (needs the R the sums were taken at): 28 lanes of warp 0, which also hold
-  // red.total.  CTAs that did not gather (they wait for CTA 0's sums below) skip it.
-  const bool grid_exchange = p.persistent && grid_x > 1 && !p.gather_direct;
-  const bool has_total = !grid_exchange || blockIdx.x == 0;
-  if (KIND != kNdt3 && warp == 0 && has_total) {
-    __syncwarp();
-    double canon = 0.0;
-    if (lane < kAcc6) canon = Canonical6Entry(lane, red.total, st.R);
-    __syncwarp();
-    if (lane < kAcc6) red.total[lane] = canon;
-  }
-  NLO_STAMP(10);
-  // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs (the pushing
-  // CTA stores into the slot of every rank, every CTA of every rank polls its local slots and
-  // adds them in rank order => bit-identical sums and steps everywhere), through the local slot
-  // when CTA 0 gathered on behalf of the grid.
+  // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs, through the
+  // local slot when CTA 0 gathered on behalf of the grid.
   if (p.use_peer || grid_exchange) {
-    const bool pusher = has_total;
+    const bool pusher = grid_x == 1 || blockIdx.x == 0;
+    if (pusher && KIND != kNdt3 && warp == 0)  // raw -> canonical, by warp 0 (which holds red.total)
+      CanonicalRotate(red.total, st.R, &red.gather_lanes[0][0], plan, lane);
+    canonical_done = true;
     // one exchange per loop iteration in every launch shape that exchanges
     const unsigned long long seq = red.seq0 + static_cast<unsigned long long>(it) + 1ULL;
     unsigned int xtag;
@@ -411,23 +383,31 @@ __device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterPara
       src = slot;
       if (pusher && tid < NACC) StoreLL(slot + 2 * tid, red.total[tid], xtag);
     }
-    __syncthreads();  // gather_lanes is reused
-    GatherLL<NACC>(src, kPeerWords, nsrc, xtag, p.use_peer ? kPeerTimeoutNs : kGridTimeoutNs,
-                   red.gather_lanes, red.total, &red.fail);
+    if (leader) {
+      __syncthreads();  // gather_lanes is reused
+      GatherLL<NACC>(src, kPeerWords, nsrc, xtag, p.use_peer ? kPeerTimeoutNs : kGridTimeoutNs,
+                     red.gather_lanes, red.total, &red.fail);
+    }
     if (tid == 0) {
       red.exchanges += 1;
       if (p.use_peer && red.fail && pusher) *p.peer.error = 1;
     }
   }
-  if (red.fail) return kReduceFailed;
-  if (p.mode == kModeAssemble) {
-    if (warp == 0) {
-      __syncwarp();
-      if (lane < NACC && writer) p.sums[problem * 32 + lane] = red.total[lane];
+  if (csize > 1) {
+    // rank 0 -> the other CTAs of the cluster: the totals (and whether a wait expired)
+    if (leader && tid < NACC) {
+      const double v = red.total[tid];  // written by this thread
+      for (unsigned int r = 1; r < csize; ++r) StoreClusterF64(&red.total[tid], r, v);
     }
-    return kReduceAssembled;
+    if (leader && tid == 0 && red.fail)
+      for (unsigned int r = 1; r < csize; ++r) StoreClusterU32(&red.fail, r, 1u);
+    ClusterSync();
   }
-  return kReduceStep;
+  NLO_STAMP(9);
+  if (!canonical_done && KIND != kNdt3 && warp == 0)
+    CanonicalRotate(red.total, st.R, &red.gather_lanes[0][0], plan, lane);
+  NLO_STAMP(10);
+  return red.fail ? kReduceFailed : kReduceStep;
 }
 
 // The damped step of one iteration on the canonical sums in red.total: warp 0 of the CTA, lane 0
@@ -460,30 +440,82 @@ __device__ __forceinline__ void StepPhase(ReduceArea& red, const IterParams& p, 
 // Reduction, exchange and step of iteration `it`, called by all threads of the CTA after the tile
 // loop; returns a ReduceOutcome.
 template <int KIND>
-__device__ __forceinline__ int PostTileBody(ReduceArea& red, const IterParams& p, State* st_global, int it) {
-  const int outcome = ReduceAndExchange<KIND>(red, p, it);
+__device__ __forceinline__ int PostTileBody(ReduceArea& red, const IterParams& p, const CanonPlan& plan,
+                                            State* st_global, int it) {
+  const int outcome = ReduceAndExchange<KIND>(red, p, plan, it);
   NLO_STAMP(11);
   if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(red, p, st_global, it);
   return outcome;
 }
-// The streaming kernel's tile loop uses all 128 registers of its 2-CTAs-per-SM budget, and ptxas
-// budgets a directly called (or inlined) function together with its caller, which pushes dozens of
-// spills into the tile loop.  It therefore calls this non-inlined copy through a pointer the
-// compiler cannot see through: a plain ABI call, the callee saves what it uses, the tile loop keeps
-// its registers.  The price (~1 us per iteration: call, register saves, generic addressing) only
-// matters for latency-bound registrations, which run the resident kernel below instead.
-template <int KIND>
-__device__ __noinline__ int PostTilePhase(ReduceArea& red, const IterParams& p, State* st_global, int it) {
-  return PostTileBody<KIND>(red, p, st_global, it);
+// ------------------------------------------------------------------ streaming kernel
+// The kernel for scans that do not fit the shared memory of the grid: tiles stream through a TMA /
+// mbarrier ring, 2 CTAs per SM, 128 registers -- all of which the tile loop uses.  Its
+// per-iteration exchange is the leader form: every CTA stores its partial and arrives on a
+// counter, CTA 0 sums them in fixed order, [all-reduces over NVLink], steps and publishes the new
+// state as LL words that the other CTAs poll.  The cluster / all-gather form of the resident
+// kernel was tried here too and is slower for this shape: inlined, its code drives dozens of spills
+// into the tile loop (ptxas budgets inlined and directly called code together with the loop);
+// called through a pointer, the ABI register saves of 75 000 threads per iteration go straight to
+// L2 (the L1 left beside 2 x 104 KB of stages is ~40 KB) and cost 9 - 18 us per iteration
+// (1 M points: 30.8 against 22.1 us; 16 M: 238.7 against 220.4 us, same box).
+__device__ __noinline__ void Step6Call(const double* __restrict__ sums, State* st, double ptol, double gtol,
+                                       int max_iterations, double* trace_row) {
+  Step6(sums, st, ptol, gtol, max_iterations, trace_row);
 }
 
-template <int KIND>
-__device__ __noinline__ void StepOnlyPhase(ReduceArea& red, const IterParams& p, State* st_global, int it) {
-  StepPhase<KIND>(red, p, st_global, it);
+// One-shot all-reduce of `total[0..nacc)` over peer-mapped buffers; called by all threads of the
+// finalising CTA.  "LL" wire format: every 8-byte word carries 4 bytes of payload and the 4-byte
+// sequence number of the exchange, so a word is valid the moment its sequence matches -- one
+// NVLink one-way latency, no fences, no separate flag.  A double travels as two words.  Slots are
+// double-buffered by sequence parity (a rank can only be one exchange ahead of a peer).  The sum
+// runs in rank order 0..n-1 on every rank => bit-identical results everywhere.
+__device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc) {
+  __shared__ unsigned int halves[kMaxRanks][kPeerWords];
+  const int tid = threadIdx.x;
+  const unsigned long long seq = *pc.seq + 1;
+  const unsigned int seq32 = static_cast<unsigned int>(seq);
+  const int parity = static_cast<int>(seq & 1ULL);
+  const int words = 2 * nacc;
+  if (tid < words) {
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(total[tid >> 1]));
+    const unsigned long long half = (tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
+    const unsigned long long word = (static_cast<unsigned long long>(seq32) << 32) | half;
+    const int slot = (parity * kMaxRanks + pc.rank) * kPeerWords + tid;
+    for (int r = 0; r < pc.nranks; ++r)
+      *reinterpret_cast<volatile unsigned long long*>(pc.slots[r] + slot) = word;
+    SpinWatch watch;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const volatile unsigned long long* src =
+          reinterpret_cast<const volatile unsigned long long*>(pc.slots[pc.rank]) +
+          (parity * kMaxRanks + r) * kPeerWords + tid;
+      unsigned long long w = *src;
+      while (static_cast<unsigned int>(w >> 32) != seq32) {
+        if (watch.Expired(kPeerTimeoutNs)) {  // a peer died; fail instead of hanging
+          *pc.error = 1;
+          break;
+        }
+        w = *src;
+      }
+      halves[r][tid] = static_cast<unsigned int>(w);
+    }
+  }
+  __syncthreads();
+  if (tid < nacc) {
+    double s = 0.0;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const unsigned long long bits = (static_cast<unsigned long long>(halves[r][2 * tid + 1]) << 32) |
+                                      static_cast<unsigned long long>(halves[r][2 * tid]);
+      s += __longlong_as_double(static_cast<long long>(bits));
+    }
+    total[tid] = s;
+  }
+  if (tid == 0) *pc.seq = seq;
+  __syncthreads();
 }
+
 
 template <int KIND, int LOSS, typename ST>
-__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const __grid_constant__ IterParams p) {
+__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = PlanesOf<KIND, ST>();
@@ -512,11 +544,6 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const __grid_
       FenceBarrierInit();
     }
     st = *st_global;
-    sm.red.fail = 0;
-    // sequence number of the peer exchange buffers (monotonic across launches) and exchanges made;
-    // kept in shared memory: the tile loop has no register to spare
-    sm.red.seq0 = p.use_peer ? *p.peer.seq : 0ULL;
-    sm.red.exchanges = 0;
   }
   __syncthreads();
 
@@ -650,39 +677,171 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const __grid_
       NLO_STAMP(1);
       __syncthreads();
       NLO_STAMP(2);
-      int (*volatile post_fn)(ReduceArea&, const IterParams&, State*, int) = &PostTilePhase<KIND>;
-      const int outcome = post_fn(sm.red, p, st_global, it);
-      if (outcome == kReduceLeave) return;
-      if (outcome == kReduceFailed) {  // a wait expired (GPU shared or preempted, a rank died): leave, do not hang
-        if (tid == 0) {
-          st.status = 2;
-          st.done = 1;
-          if (writer) *st_global = st;
+
+      // CTA sum over the 8 consumer warps, fixed order
+      if (tid < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) s += sm.red.warp_sums[w][tid];
+        sm.red.total[tid] = s;
+      }
+      if (grid_x > 1) {
+        // per-CTA partial -> HBM/L2; double-buffered by iteration parity for the persistent path
+        double* partial_base =
+            p.partials + static_cast<size_t>((it & 1) * gridDim.y + problem) * grid_x * NACC;
+        if (tid < NACC) {
+          __stcg(partial_base + static_cast<size_t>(blockIdx.x) * NACC + tid, sm.red.total[tid]);
+          // persistent path: thread 0's releasing fence after the bar.sync below covers these
+          // stores by cumulativity; the ticket path fences per writer
+          if (!p.persistent) __threadfence();
+        }
+        if (p.persistent) {
+          // Persistent grid: every CTA arrives on a counter; CTA 0 (the leader) waits for all
+          // partials, reduces them, [all-reduces over NVLink], steps and PUBLISHES the new 160-byte
+          // state as 40 "LL" words (32 payload bits + the iteration number in one 8-byte store, so
+          // a word is valid the moment its number matches: no fence, no separate flag); the other
+          // CTAs poll those words -- one L2 round trip after the leader's stores -- and rebuild
+          // the state.
+          constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
+          unsigned int* counter = reinterpret_cast<unsigned int*>(p.ll_sums + problem * kSyncStride);
+          unsigned long long* ll_state = p.ll_sums + problem * kSyncStride + 8;
+          const unsigned int want = static_cast<unsigned int>(it) + 1u;
+          __syncthreads();
+          if (tid == 0) {
+            __threadfence();  // releases this CTA's partial (cumulative over the bar.sync above)
+            atomicAdd(counter, 1u);
+            sm.red.flag = 1;
+          }
+          SpinWatch watch;
+          if (blockIdx.x == 0) {
+            if (tid == 0) {
+              while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
+                if (watch.Expired(kGridTimeoutNs)) { sm.red.flag = 0; break; }
+              __threadfence();
+            }
+            __syncthreads();
+            if (sm.red.flag == 0) {  // a CTA went missing (cannot happen under a cooperative launch)
+              if (tid == 0) { st.status = 2; st.done = 1; *st_global = st; }
+              __syncthreads();
+              if (tid < kStateWords) {  // still publish, so that the other CTAs leave as well
+                const unsigned long long bits = static_cast<unsigned long long>(
+                    __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
+                __stcg(ll_state + tid, (static_cast<unsigned long long>(want) << 32) |
+                                           ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
+              }
+              break;
+            }
+          } else {
+            __syncthreads();  // sm.red.flag = 1 visible
+            if (tid < kStateWords) {
+              const volatile unsigned long long* src = ll_state + tid;
+              unsigned long long w = *src;
+              while (static_cast<unsigned int>(w >> 32) != want) {
+                if (watch.Expired(kGridTimeoutNs)) { sm.red.flag = 0; break; }
+                w = *src;
+              }
+              sm.red.halves[tid] = static_cast<unsigned int>(w);
+            }
+            __syncthreads();
+            if (sm.red.flag == 0) {  // the leader went missing
+              if (tid == 0) { st.status = 2; st.done = 1; }
+              __syncthreads();
+              break;
+            }
+            if (tid < kStateWords / 2)
+              reinterpret_cast<double*>(&st)[tid] = __longlong_as_double(static_cast<long long>(
+                  (static_cast<unsigned long long>(sm.red.halves[2 * tid + 1]) << 32) | sm.red.halves[2 * tid]));
+            __syncthreads();
+            continue;
+          }
+        } else {
+          __syncthreads();
+          if (tid == 0) {
+            const unsigned int ticket = atomicAdd(p.tickets + problem, 1u);
+            sm.red.flag = (ticket == static_cast<unsigned int>(grid_x) - 1u) ? 1 : 0;
+            if (sm.red.flag) p.tickets[problem] = 0u;  // ready for the next launch
+          }
+          __syncthreads();
+          if (sm.red.flag == 0) return;  // only the last CTA to arrive carries on
+          __threadfence();
+        }
+        NLO_STAMP(3);
+        // cross-CTA sum: thread (j, l8) adds CTAs l8, l8+8, ...; then the 8 lanes in order
+        const int j = tid >> 3, l8 = tid & 7;
+        if (j < NACC) {
+          const double* base = partial_base + j;
+          double s = 0.0;
+          int g = l8;
+          // loads are issued 16 at a time (independent addresses, the tail predicated so that it
+          // costs one round trip instead of one per element); the adds keep the fixed order
+          for (; g < grid_x; g += 128) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int c = g + 8 * u;
+              v[u] = c < grid_x ? __ldcg(base + static_cast<size_t>(c) * NACC) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s += v[u];
+          }
+          sm.red.warp_sums[l8][j] = s;
         }
         __syncthreads();
-        break;
+        if (tid < NACC) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += sm.red.warp_sums[w][tid];
+          sm.red.total[tid] = s;
+        }
       }
-      if (outcome == kReduceAssembled) break;
+      __syncthreads();
+
+      NLO_STAMP(4);
+      // raw -> canonical (needs the R the sums were taken at), by warp 0
+      if (KIND != kNdt3 && warp == 0) {
+        const CanonPlan plan = MakeCanonPlan(lane);
+        CanonicalRotate(sm.red.total, st.R, &sm.red.gather_lanes[0][0], plan, lane);
+      }
+      __syncthreads();
+      if (p.use_peer) PeerAllReduce(p.peer, sm.red.total, NACC);
+      if (p.mode == kModeAssemble) {
+        if (tid < NACC && writer) p.sums[problem * 32 + tid] = sm.red.total[tid];
+        return;
+      }
     } else {
       if (tid < NACC) sm.red.total[tid] = p.sums[problem * 32 + tid];
-      if (warp == 0) {
-        void (*volatile step_fn)(ReduceArea&, const IterParams&, State*, int) = &StepOnlyPhase<KIND>;
-        step_fn(sm.red, p, st_global, it);
+      __syncthreads();
+    }
+
+    // ---------------- damped step by warp 0 (redundantly per CTA in the persistent path)
+    if (warp == 0) {
+      double* trace_row = nullptr;
+      if (p.trace != nullptr && writer)
+        trace_row = p.trace + (static_cast<size_t>(problem) * p.max_iterations + st.iteration) *
+                                  T::kTrace;
+      if (lane == 0) {
+        if (KIND == kNdt3)
+          Step3(sm.red.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+                trace_row);
+        else
+          Step6Call(sm.red.total, &st, p.parameter_tolerance, p.gradient_tolerance, p.max_iterations,
+                trace_row);
       }
+      if (lane == 0 && writer) *st_global = st;
     }
     NLO_STAMP(5);
     __syncthreads();
-    NLO_STAMP(6);
-    if (p.debug_all_ctas && it == 0 && tid == 0 && blockIdx.y == 0 && blockIdx.x < kDebugCtas && p.debug_times != nullptr) {
-      unsigned int smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.debug_times[(static_cast<size_t>(blockIdx.x) * kDebugIterations) * kDebugSlots + 7] = smid;
+    if (p.persistent && grid_x > 1 && p.mode == kModeSolve) {  // leader: publish the new state
+      constexpr int kStateWords = 2 * static_cast<int>(sizeof(State) / sizeof(double));
+      if (tid < kStateWords) {
+        const unsigned long long bits = static_cast<unsigned long long>(
+            __double_as_longlong(reinterpret_cast<const double*>(&st)[tid >> 1]));
+        __stcg(p.ll_sums + problem * kSyncStride + 8 + tid,
+               (static_cast<unsigned long long>(it + 1) << 32) |
+                   ((tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL)));
+      }
     }
-  }
-  if (p.use_peer && tid == 0 && sm.red.exchanges > 0) {
-    const bool grid_exchange = p.persistent && grid_x > 1 && !p.gather_direct;
-    if (!grid_exchange || blockIdx.x == 0)
-      *p.peer.seq = sm.red.seq0 + static_cast<unsigned long long>(sm.red.exchanges);
+    NLO_STAMP(6);
   }
   // a prefetch may still be in flight when the loop ends early: let it land before the CTA exits
   if (prefetched > 0) {
@@ -769,6 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
       ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
   };
 
+  const CanonPlan canon_plan = MakeCanonPlan(lane);  // what this lane does in the rotation to the canonical frame
   for (int it = 0; it < p.iterations_in_kernel; ++it) {
     if (st.done) break;  // uniform: every CTA steps the same state
     NLO_STAMP(0);
@@ -787,27 +947,25 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
 #pragma unroll
       for (int k = 0; k < 3; ++k) t[k] = st.t[k];
     }
-    int m = 0;
-    for (; m + 1 < my_tiles; m += 2) {  // two independent correspondences in flight per thread
+    // Two independent correspondences in flight per thread; an odd tile count pairs the last tile
+    // with itself, masked out (one loop body: the code has to stay small, see GatherLL).
+#pragma unroll 1
+    for (int m = 0; m < my_tiles; m += 2) {
+      const bool pair = m + 1 < my_tiles;
+      const int mb = pair ? m + 1 : m;
       double va[NPLANES], vb[NPLANES];
 #pragma unroll
       for (int pl = 0; pl < NPLANES; ++pl) {
         va[pl] = stages[m][pl][tid];
-        vb[pl] = stages[m + 1][pl][tid];
+        vb[pl] = stages[mb][pl][tid];
       }
       double accb[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) accb[k] = 0.0;
       one_point(va, R, t, valid_in(m), acc);
-      one_point(vb, R, t, valid_in(m + 1), accb);
+      one_point(vb, R, t, pair && valid_in(mb), accb);
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] += accb[k];
-    }
-    if (m < my_tiles) {
-      double va[NPLANES];
-#pragma unroll
-      for (int pl = 0; pl < NPLANES; ++pl) va[pl] = stages[m][pl][tid];
-      one_point(va, R, t, valid_in(m), acc);
     }
     // warp reduction by recursive halving (see the streaming kernel): lane l ends with value l
     {
@@ -831,7 +989,7 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
     NLO_STAMP(1);
     __syncthreads();
     NLO_STAMP(2);
-    const int outcome = PostTileBody<KIND>(sm.red, p, st_global, it);
+    const int outcome = PostTileBody<KIND>(sm.red, p, canon_plan, st_global, it);
     if (outcome == kReduceFailed) {
       if (tid == 0) {
         st.status = 2;

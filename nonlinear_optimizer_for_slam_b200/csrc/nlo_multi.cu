@@ -188,8 +188,13 @@ int CreateContext(const int* devices, int n, nlo_context** out) {
     sub->device_share = m;
     if (m > 1) {  // several cooperative cluster launches do not reliably co-schedule on one device
       sub->cluster_small = 1;
-      sub->cluster_big = 1;
     }
+  }
+  bool shared = false;
+  for (nlo_context* sub : ctx->subs) shared = shared || sub->device_share > 1;
+  if (shared) {
+    ctx->launch_barrier = new HostBarrier(n);
+    for (nlo_context* sub : ctx->subs) sub->launch_barrier = ctx->launch_barrier;
   }
   ctx->sm_count = ctx->subs[0]->sm_count;
   ctx->grid_single = ctx->subs[0]->grid_single;
@@ -257,6 +262,7 @@ void DestroyContext(nlo_context* ctx) {
   }
   for (nlo_context* sub : ctx->subs) nlo_context_destroy(sub);
   ctx->subs.clear();
+  delete ctx->launch_barrier;
   delete ctx;
 }
 
@@ -503,6 +509,11 @@ int Solve(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_options* 
   std::vector<std::array<double, 16>> pose(static_cast<size_t>(D));
   std::vector<nlo_solve_result> res(static_cast<size_t>(D));
   for (int r = 0; r < D; ++r) memcpy(pose[static_cast<size_t>(r)].data(), poses, 16 * sizeof(double));
+  if (trace != nullptr && options->max_iterations > 0) {  // allocate before any shard's kernel runs (see EnsureTrace)
+    const size_t need = static_cast<size_t>(options->max_iterations) * ((kind == kNdt3) ? NLO_TRACE3 : NLO_TRACE6);
+    rc = EnsureTrace(ctx->subs[0], pr->shards[0], need);
+    if (rc != NLO_OK) return Fail(ctx, rc, ctx->subs[0]->error);
+  }
   rc = ForEach(ctx, [&](int r) {
     nlo_problem* shard = pr->shards[static_cast<size_t>(r)];
     const int64_t sb = pr->shard_begin[static_cast<size_t>(r)];

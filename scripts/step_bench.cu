@@ -65,12 +65,14 @@ __global__ void bench(const double* sums_in, long long* cycles, double* out, int
   }
   t1 = clock64();
   if (lane == 0) cycles[4] = (t1 - t0) / reps;
-  // 3: canonical rotation, one entry per lane
+  // 3: canonical rotation, planned two-round form (in place on a scratch copy of the sums)
+  __shared__ double canon_sums[32], canon_scratch[9];
+  if (lane < 28) canon_sums[lane] = sums[lane];
+  const CanonPlan plan = MakeCanonPlan(lane);
   t0 = clock64();
   for (int r = 0; r < reps; ++r) {
-    double c = 0.0;
-    if (lane < 28) c = Canonical6Entry(lane, sums, st.R);
-    acc += c;
+    CanonicalRotate(canon_sums, st.R, canon_scratch, plan, lane);
+    acc += canon_sums[lane & 15];
     __syncwarp();
   }
   t1 = clock64();
