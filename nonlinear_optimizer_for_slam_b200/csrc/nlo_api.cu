@@ -162,11 +162,11 @@ GridPlan PlanPersistentGrid(nlo_context* ctx, const nlo_problem* pr, int kind, i
   return plan;
 }
 
-// Tag base of the next persistent launch on this problem: the solve epoch in the upper 16 bits, so
+// Tag base of the next resident launch on this problem: the solve epoch in bits 16..30, so
 // that LL words left by earlier solves never match.  When the epoch wraps the buffers are cleared.
 int NextEpoch(nlo_context* ctx, nlo_problem* pr, unsigned int* tag_base) {
   pr->epoch += 1;
-  if (pr->epoch > 65535u) {
+  if (pr->epoch > 32767u) {  // 15 bits: bit 31 of a tag marks a failed wait
     pr->epoch = 1;
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_ll_partials, 0, pr->ll_partials_bytes, ctx->stream));
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(pr->num_problems + 1) * kSyncStride * sizeof(unsigned long long),

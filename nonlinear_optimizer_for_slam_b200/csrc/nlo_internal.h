@@ -209,7 +209,9 @@ struct MapAccumParams {
   int dims[3];
   double voxel;
   int* count;       // [cells]
-  double* sums;     // [cells][9]: sum d (3) | moment d d^T: xx xy xz yy yz zz (6), d = p - voxel centre
+  double* sums;     // [cells][9] 64-bit FIXED-POINT words (fixed_shift fractional bits): sum d (3) | moment d d^T:
+                    // xx xy xz yy yz zz (6), d = (p - voxel centre) / voxel in [-1/2, 1/2]
+  int fixed_shift;  // min(40, 61 - bits(n)): n points cannot overflow 63 bits
   unsigned long long* keys;  // hashed: [slots], kHashEmpty-initialised; cells = slots
   long long hash_mask;
 };

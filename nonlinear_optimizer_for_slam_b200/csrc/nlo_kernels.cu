@@ -146,7 +146,6 @@ __host__ __device__ constexpr int PlanesOf() {
 struct ReduceArea {
   double warp_sums[8][kAcc6];     // sums of the 8 consumer warps
   double gather_lanes[8][kAcc6];  // the 8 strided lanes of a cross-CTA / cross-cluster / cross-rank sum
-  double cluster_part[2][kMaxCluster][kAcc6];  // rank-0 CTA of a cluster: the sums of its CTAs (by iteration parity)
   double total[32];               // reduced (raw, then canonical) sums
   State state;                    // CTA-local copy of the registration state
   unsigned long long seq0;        // peer exchange sequence number at kernel start
@@ -154,6 +153,18 @@ struct ReduceArea {
   unsigned int halves[kPeerWords];  // streaming kernel: payload halves of the published state (LL words)
   int flag;
   int fail;                       // a polled wait expired
+};
+
+// Shared memory of the resident kernel in front of its stages.
+constexpr int kStageRecords = 48;  // cluster partials a leader CTA gathers in one go (NLO_DIRECT_MAX <= this)
+struct ResidentSmem {
+  ReduceArea red;
+  double stage[kStageRecords][kAcc6];  // gathered cluster partials, before they are added in fixed order
+  // LL words exchanged inside a thread-block cluster through distributed shared memory, by
+  // iteration parity: the sums of the cluster's CTAs (rank-0 CTA only) and the totals rank 0 returns
+  unsigned long long cl_in[2][kMaxCluster][kAcc6][2];
+  unsigned long long cl_out[2][kAcc6][2];
+  uint64_t full;  // all tiles of this CTA have landed
 };
 
 // ST = storage type of the planes in HBM and in the stages: double (parity mode, 96 B per NDT
@@ -211,10 +222,22 @@ __device__ __forceinline__ void StoreClusterF64(double* local, unsigned int targ
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
 }
 
-__device__ __forceinline__ void StoreClusterU32(int* local, unsigned int target_rank, unsigned int v) {
+// LL words in (distributed) shared memory: the two 8-byte words of a double, each carrying the tag.
+// The writer stores into the copy of `local` that CTA `target_rank` of the cluster holds; the
+// reader polls its own shared memory -- no hardware barrier, no L2.
+__device__ __forceinline__ void StoreClusterLL(unsigned long long* local, unsigned int target_rank, double v,
+                                               unsigned int tag) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(SmemAddr(local)), "r"(target_rank));
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+  asm volatile("st.relaxed.cluster.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(remote), "l"(t | (bits & 0xffffffffULL)),
+               "l"(t | (bits >> 32))
+               : "memory");
+}
+__device__ __forceinline__ void LoadSharedLL(const unsigned long long* local, unsigned long long& lo,
+                                             unsigned long long& hi) {
+  asm volatile("ld.relaxed.cluster.shared::cta.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(SmemAddr(local)) : "memory");
 }
 
 // ------------------------------------------------------------------ "LL" words
@@ -222,15 +245,34 @@ __device__ __forceinline__ void StoreClusterU32(int* local, unsigned int target_
 // valid the moment its tag matches: one store, one (polled) load, no fence, no separate flag --
 // one L2 round trip inside a GPU, one NVLink one-way latency between GPUs.  The two words of a
 // double are adjacent (one 16-byte store / load; each half is validated on its own).
-__device__ __forceinline__ void StoreLL(unsigned long long* dst, double v, unsigned int tag) {
+// Scope: words exchanged inside one GPU use gpu-scope relaxed accesses, served by the L2; words that
+// cross NVLink use system scope (`sys`).
+__device__ __forceinline__ void StoreLL(unsigned long long* dst, double v, unsigned int tag, bool sys) {
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
   const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
   const unsigned long long lo = t | (bits & 0xffffffffULL), hi = t | (bits >> 32);
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+  if (sys)
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+  else
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
 }
 __device__ __forceinline__ void LoadLL(const unsigned long long* src, unsigned long long& lo,
-                                       unsigned long long& hi) {
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+                                       unsigned long long& hi, bool sys) {
+  if (sys)
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+  else
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+}
+
+__device__ __forceinline__ unsigned int LoadGpuU32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long LoadGpuU64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // Fixed-order sum of `n_src` LL records of NACC doubles (record c at base + c * stride_words):
@@ -242,7 +284,7 @@ __device__ __forceinline__ void LoadLL(const unsigned long long* src, unsigned l
 // instruction cache of the SM, a miss per 128-byte line of cold code costs more than the math.
 template <int NACC>
 __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
-                                      unsigned int tag, unsigned long long timeout_ns,
+                                      unsigned int tag, bool sys, unsigned long long timeout_ns,
                                       double (*lanes)[kAcc6], double* total, int* fail) {
   const int tid = threadIdx.x;
   const int j = tid >> 3, l8 = tid & 7;
@@ -252,24 +294,76 @@ __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride
     const unsigned long long* src = base + static_cast<size_t>(l8) * stride_words + 2 * j;
     const size_t step = static_cast<size_t>(8) * stride_words;
     unsigned long long lo, hi, nlo = 0ULL, nhi = 0ULL;
-    if (l8 < n_src) LoadLL(src, lo, hi);
+    if (l8 < n_src) LoadLL(src, lo, hi, sys);
 #pragma unroll 1
     for (int c = l8; c < n_src; c += 8) {
       const bool more = c + 8 < n_src;
-      if (more) LoadLL(src + step, nlo, nhi);  // the next record travels while this one is checked
+      if (more) LoadLL(src + step, nlo, nhi, sys);  // the next record travels while this one is checked
       while (static_cast<unsigned int>(lo >> 32) != tag || static_cast<unsigned int>(hi >> 32) != tag) {
         if (watch.Expired(timeout_ns)) {
           *fail = 1;
           lo = hi = static_cast<unsigned long long>(tag) << 32;
           break;
         }
-        LoadLL(src, lo, hi);
+        LoadLL(src, lo, hi, sys);
       }
       s += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
       src += step;
       lo = nlo;
       hi = nhi;
     }
+    lanes[l8][j] = s;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += lanes[w][tid];
+    total[tid] = s;
+  }
+}
+
+// The same sum for up to kStageRecords records with every load in flight at once: thread t takes one
+// (record, four consecutive values) item -- 33 records x 7 quads are 231 of the 256 threads -- polls
+// its four words until they carry the tag and parks the doubles in `stage`; the additions then run
+// over shared memory in exactly the order of GatherLL (records l8, l8+8, ... per lane, lanes in
+// order), so both give the same bits.  One L2 round trip after the last record lands instead of
+// one per record of a lane.
+template <int NACC>
+__device__ __noinline__ void GatherStaged(const unsigned long long* base, int stride_words, int n_src,
+                                          unsigned int tag, unsigned long long timeout_ns, double (*stage)[kAcc6],
+                                          double (*lanes)[kAcc6], double* total, int* fail) {
+  constexpr int kQuads = (NACC + 3) / 4;
+  const int tid = threadIdx.x;
+  SpinWatch watch;
+#pragma unroll 1
+  for (int item = tid; item < n_src * kQuads; item += kThreads) {
+    const int c = item / kQuads, j0 = 4 * (item - c * kQuads);
+    const unsigned long long* src = base + static_cast<size_t>(c) * stride_words + 2 * j0;
+    unsigned long long lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (j0 + k < NACC) LoadLL(src + 2 * k, lo[k], hi[k], false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (j0 + k < NACC) {
+        while (static_cast<unsigned int>(lo[k] >> 32) != tag || static_cast<unsigned int>(hi[k] >> 32) != tag) {
+          if (watch.Expired(timeout_ns)) {
+            *fail = 1;
+            lo[k] = hi[k] = static_cast<unsigned long long>(tag) << 32;
+            break;
+          }
+          LoadLL(src + 2 * k, lo[k], hi[k], false);
+        }
+        stage[c][j0 + k] = __longlong_as_double(static_cast<long long>((hi[k] << 32) | (lo[k] & 0xffffffffULL)));
+      }
+    }
+  }
+  __syncthreads();
+  const int j = tid >> 3, l8 = tid & 7;
+  if (j < NACC) {
+    double s = 0.0;
+    for (int c = l8; c < n_src; c += 8) s += stage[c][j];
     lanes[l8][j] = s;
   }
   __syncthreads();
@@ -296,24 +390,27 @@ enum ReduceOutcome : int {
 };
 
 // Everything between the tile loop and the damped step of iteration `it` in the resident kernel.
-//  1. CTA sum (fixed order over the 8 warps); the CTAs of a thread-block cluster hand their 28
-//     sums to the cluster's rank-0 CTA through distributed shared memory and meet at the hardware
-//     cluster barrier; rank 0 adds them in rank order and stores the cluster's partial as "LL"
-//     words (32 payload bits + the tag of this iteration per 8-byte store: a word is valid the
-//     moment its tag matches -- no counter, no fence).
+//  1. CTA sum (fixed order over the 8 warps).  The CTAs of a thread-block cluster hand their 28 sums
+//     to the cluster's rank-0 CTA as LL words in ITS shared memory (distributed shared memory: 32
+//     payload bits + the tag of this iteration per 8-byte store, valid the moment the tag matches);
+//     rank 0 polls its own shared memory, adds them in rank order and stores the cluster's partial,
+//     LL words again, to global memory.  No hardware barrier, no counter, no fence.
 //  2. Only the rank-0 CTAs poll global memory.  gather_direct (few clusters): every rank-0 CTA
 //     gathers all cluster partials and adds them in cluster order.  Otherwise CTA 0 gathers,
 //     rotates to the canonical frame and stores the sums (LL again) into the local slot -- or,
 //     sharded across GPUs, into the slot of every rank over NVLink -- and the rank-0 CTAs gather
 //     those (in rank order: bit-identical sums, and therefore steps, on every GPU).
-//  3. Rank 0 hands the totals to the other CTAs of its cluster over distributed shared memory, second
-//     cluster barrier; the other CTAs sleep in that hardware barrier meanwhile instead of polling:
-//     132 CTAs polling the same few L2 lines serialise in the L2 slices and delay the very stores
-//     they wait for (measured: 2.7 us for the all-CTAs gather of 33 partials).
+//  3. Rank 0 hands the totals to the other CTAs of its cluster the same way (LL words into their
+//     shared memory), which they poll locally: 132 CTAs polling the same few L2 lines would
+//     serialise in the L2 slices and delay the very stores they wait for.
 //  4. Every CTA rotates to the canonical frame (if step 2 did not) and steps its own copy of the state.
+// A wait that expires is flagged in red.fail and travels to the cluster as a tag with bit 31 set.
+constexpr unsigned int kFailTagBit = 0x80000000u;
+
 template <int KIND>
-__device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterParams& p, const CanonPlan& plan, int it) {
+__device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterParams& p, const CanonPlan& plan, int it) {
   constexpr int NACC = KindTraits<KIND>::kAcc;
+  ReduceArea& red = sm.red;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int problem = blockIdx.y;
@@ -330,29 +427,47 @@ __device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterPara
   const unsigned int csize = ClusterSize(), crank = ClusterCtaRank();
   const bool leader = crank == 0;
   const bool grid_exchange = grid_x > 1 && !p.gather_direct;  // CTA 0 gathers on behalf of the grid
+  const int parity = it & 1;
+  const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;  // bit 31 clear
   bool canonical_done = false;
   if (grid_x == 1) {
     if (tid < NACC) red.total[tid] = cta_sum;
     NLO_STAMP(3);
   } else {
     const int n_clusters = static_cast<int>(ClusterCountX()), cluster_id = static_cast<int>(ClusterIdX());
-    const int parity = it & 1;
-    const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;
     unsigned long long* row_partials =
         p.ll_partials + static_cast<size_t>(parity * gridDim.y + problem) * n_clusters * (2 * NACC);
-    if (csize > 1) {
-      if (tid < NACC) StoreClusterF64(&red.cluster_part[parity][crank][tid], 0u, cta_sum);
-      ClusterSync();
-      if (leader && tid < NACC) {
-        cta_sum = 0.0;
-        for (unsigned int r = 0; r < csize; ++r) cta_sum += red.cluster_part[parity][r][tid];
+    if (csize > 1 && tid < NACC) {
+      if (!leader) {
+        StoreClusterLL(&sm.cl_in[parity][crank][tid][0], 0u, cta_sum, tag);
+      } else {
+        SpinWatch watch;
+        for (unsigned int r = 1; r < csize; ++r) {  // rank order
+          unsigned long long lo, hi;
+          LoadSharedLL(&sm.cl_in[parity][r][tid][0], lo, hi);
+          while (static_cast<unsigned int>(lo >> 32) != tag || static_cast<unsigned int>(hi >> 32) != tag) {
+            if (watch.Expired(kGridTimeoutNs)) {
+              red.fail = 1;
+              lo = hi = 0ULL;
+              break;
+            }
+            LoadSharedLL(&sm.cl_in[parity][r][tid][0], lo, hi);
+          }
+          cta_sum += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
+        }
       }
     }
     if (leader && tid < NACC)
-      StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag);
+      StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag, false);
     NLO_STAMP(3);
-    if (grid_exchange ? blockIdx.x == 0 : leader)
-      GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, kGridTimeoutNs, red.gather_lanes, red.total, &red.fail);
+    if (grid_exchange ? blockIdx.x == 0 : leader) {
+      if (n_clusters <= kStageRecords)
+        GatherStaged<NACC>(row_partials, 2 * NACC, n_clusters, tag, kGridTimeoutNs, sm.stage, red.gather_lanes,
+                           red.total, &red.fail);
+      else
+        GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, false, kGridTimeoutNs, red.gather_lanes, red.total,
+                       &red.fail);
+    }
   }
   NLO_STAMP(4);
   // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs, through the
@@ -374,18 +489,18 @@ __device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterPara
       src = p.peer.slots[p.peer.rank] + static_cast<size_t>(xpar) * kMaxRanks * kPeerWords;
       if (pusher && tid < NACC) {  // the thread that holds red.total[tid]
         const size_t slot = (static_cast<size_t>(xpar) * kMaxRanks + p.peer.rank) * kPeerWords + 2 * tid;
-        for (int r = 0; r < nsrc; ++r) StoreLL(p.peer.slots[r] + slot, red.total[tid], xtag);
+        for (int r = 0; r < nsrc; ++r) StoreLL(p.peer.slots[r] + slot, red.total[tid], xtag, true);
       }
     } else {
-      xtag = p.tag_base + static_cast<unsigned int>(it) + 1u;
+      xtag = tag;
       nsrc = 1;
-      unsigned long long* slot = p.ll_sums + (static_cast<size_t>(problem) * 2 + (it & 1)) * kPeerWords;
+      unsigned long long* slot = p.ll_sums + (static_cast<size_t>(problem) * 2 + parity) * kPeerWords;
       src = slot;
-      if (pusher && tid < NACC) StoreLL(slot + 2 * tid, red.total[tid], xtag);
+      if (pusher && tid < NACC) StoreLL(slot + 2 * tid, red.total[tid], xtag, false);
     }
     if (leader) {
       __syncthreads();  // gather_lanes is reused
-      GatherLL<NACC>(src, kPeerWords, nsrc, xtag, p.use_peer ? kPeerTimeoutNs : kGridTimeoutNs,
+      GatherLL<NACC>(src, kPeerWords, nsrc, xtag, p.use_peer != 0, p.use_peer ? kPeerTimeoutNs : kGridTimeoutNs,
                      red.gather_lanes, red.total, &red.fail);
     }
     if (tid == 0) {
@@ -394,19 +509,34 @@ __device__ __forceinline__ int ReduceAndExchange(ReduceArea& red, const IterPara
     }
   }
   if (csize > 1) {
-    // rank 0 -> the other CTAs of the cluster: the totals (and whether a wait expired)
-    if (leader && tid < NACC) {
-      const double v = red.total[tid];  // written by this thread
-      for (unsigned int r = 1; r < csize; ++r) StoreClusterF64(&red.total[tid], r, v);
+    if (leader) {
+      __syncthreads();  // red.fail of every thread is in
+      if (tid < NACC) {  // rank 0 -> the other CTAs of the cluster: the totals (red.total[tid] is this thread's)
+        const unsigned int out_tag = red.fail ? (tag | kFailTagBit) : tag;
+        const double v = red.total[tid];
+        for (unsigned int r = 1; r < csize; ++r) StoreClusterLL(&sm.cl_out[parity][tid][0], r, v, out_tag);
+      }
+    } else if (tid < NACC) {
+      SpinWatch watch;
+      unsigned long long lo, hi;
+      LoadSharedLL(&sm.cl_out[parity][tid][0], lo, hi);
+      while ((static_cast<unsigned int>(lo >> 32) & ~kFailTagBit) != tag ||
+             (static_cast<unsigned int>(hi >> 32) & ~kFailTagBit) != tag) {
+        if (watch.Expired(kGridTimeoutNs)) {
+          lo = hi = static_cast<unsigned long long>(kFailTagBit) << 32;
+          break;
+        }
+        LoadSharedLL(&sm.cl_out[parity][tid][0], lo, hi);
+      }
+      if ((lo >> 32) & kFailTagBit) red.fail = 1;
+      red.total[tid] = __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
     }
-    if (leader && tid == 0 && red.fail)
-      for (unsigned int r = 1; r < csize; ++r) StoreClusterU32(&red.fail, r, 1u);
-    ClusterSync();
   }
   NLO_STAMP(9);
   if (!canonical_done && KIND != kNdt3 && warp == 0)
     CanonicalRotate(red.total, st.R, &red.gather_lanes[0][0], plan, lane);
   NLO_STAMP(10);
+  if (csize > 1 && !leader) __syncthreads();  // red.fail set by warp 0 of a non-leader CTA
   return red.fail ? kReduceFailed : kReduceStep;
 }
 
@@ -440,11 +570,11 @@ __device__ __forceinline__ void StepPhase(ReduceArea& red, const IterParams& p, 
 // Reduction, exchange and step of iteration `it`, called by all threads of the CTA after the tile
 // loop; returns a ReduceOutcome.
 template <int KIND>
-__device__ __forceinline__ int PostTileBody(ReduceArea& red, const IterParams& p, const CanonPlan& plan,
+__device__ __forceinline__ int PostTileBody(ResidentSmem& sm, const IterParams& p, const CanonPlan& plan,
                                             State* st_global, int it) {
-  const int outcome = ReduceAndExchange<KIND>(red, p, plan, it);
+  const int outcome = ReduceAndExchange<KIND>(sm, p, plan, it);
   NLO_STAMP(11);
-  if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(red, p, st_global, it);
+  if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(sm.red, p, st_global, it);
   return outcome;
 }
 // ------------------------------------------------------------------ streaming kernel
@@ -715,7 +845,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           SpinWatch watch;
           if (blockIdx.x == 0) {
             if (tid == 0) {
-              while (*reinterpret_cast<volatile unsigned int*>(counter) < want * grid_x)
+              while (LoadGpuU32(counter) < want * grid_x)
                 if (watch.Expired(kGridTimeoutNs)) { sm.red.flag = 0; break; }
               __threadfence();
             }
@@ -734,11 +864,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           } else {
             __syncthreads();  // sm.red.flag = 1 visible
             if (tid < kStateWords) {
-              const volatile unsigned long long* src = ll_state + tid;
-              unsigned long long w = *src;
+              const unsigned long long* src = ll_state + tid;
+              unsigned long long w = LoadGpuU64(src);
               while (static_cast<unsigned int>(w >> 32) != want) {
                 if (watch.Expired(kGridTimeoutNs)) { sm.red.flag = 0; break; }
-                w = *src;
+                w = LoadGpuU64(src);
               }
               sm.red.halves[tid] = static_cast<unsigned int>(w);
             }
@@ -863,11 +993,6 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
 // inlined next to the tile loop without spilling, reads the tiles from HBM exactly once per Solve
 // (one bulk copy per tile, one mbarrier) and takes two correspondences per thread and step for
 // instruction-level parallelism on the fp64 pipe.
-struct ResidentSmem {
-  ReduceArea red;
-  uint64_t full;  // all tiles of this CTA have landed
-};
-
 template <int KIND, int LOSS>
 __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_constant__ IterParams p) {
   using T = KindTraits<KIND>;
@@ -911,7 +1036,12 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
       }
     }
   }
+  // no stale word of the cluster exchange may carry a valid tag; and no CTA may store into the
+  // shared memory of a cluster peer that has not started yet
+  for (int k = tid; k < 2 * kMaxCluster * kAcc6 * 2; k += kThreads) (&sm.cl_in[0][0][0][0])[k] = 0ULL;
+  for (int k = tid; k < 2 * kAcc6 * 2; k += kThreads) (&sm.cl_out[0][0][0])[k] = 0ULL;
   __syncthreads();
+  if (ClusterSize() > 1) ClusterSync();
   if (my_tiles > 0) MbarWait(&sm.full, 0);
 
   // validity of this thread's correspondence in each tile (only the range's first / last tile are ragged)
@@ -989,7 +1119,7 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
     NLO_STAMP(1);
     __syncthreads();
     NLO_STAMP(2);
-    const int outcome = PostTileBody<KIND>(sm.red, p, canon_plan, st_global, it);
+    const int outcome = PostTileBody<KIND>(sm, p, canon_plan, st_global, it);
     if (outcome == kReduceFailed) {
       if (tid == 0) {
         st.status = 2;
@@ -1744,24 +1874,62 @@ __global__ void map_bounds_kernel(const double* __restrict__ xyz, int64_t n, dou
 // Sums are taken about the voxel centre: the covariance is shift-invariant, and the reference's
 // raw-moment form (moment / n - mean mean^T, :255-259) loses 2 log10(|p| / voxel) digits to
 // cancellation for maps far from the origin.
+//
+// The sums are INTEGERS: an offset d = (p - centre) / voxel lies in [-1/2, 1/2], so d and d d^T are
+// accumulated as 64-bit fixed point with `fixed_shift` fractional bits (40 for up to 2 M points:
+// a resolution of 1e-12 of the voxel, far below the noise of any scan).  Integer addition is
+// associative, so the map -- and with it every registration against it -- is bit-for-bit the same
+// on every run, whatever order the atomics land in; fp64 atomics are not.  Contention: scan points
+// arrive in sweep order, so the lanes of a warp mostly share a voxel; a warp whose 32 lanes agree
+// reduces its ten values by shuffle and issues ten atomics instead of 320.
+__device__ __forceinline__ long long ToFixed(double v, int shift) {
+  return __double2ll_rn(scalbn(v, shift));
+}
+
 __global__ void map_accumulate_kernel(const MapAccumParams m) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += stride) {
-    const int ax = static_cast<int>(floor(m.xyz[3 * i] * m.inv_voxel));
-    const int ay = static_cast<int>(floor(m.xyz[3 * i + 1] * m.inv_voxel));
-    const int az = static_cast<int>(floor(m.xyz[3 * i + 2] * m.inv_voxel));
-    const double x = m.xyz[3 * i] - (ax + 0.5) * m.voxel;
-    const double y = m.xyz[3 * i + 1] - (ay + 0.5) * m.voxel;
-    const double z = m.xyz[3 * i + 2] - (az + 0.5) * m.voxel;
-    const int kx = ax - m.kmin[0], ky = ay - m.kmin[1], kz = az - m.kmin[2];
-    const int64_t c = m.keys != nullptr
-                          ? VoxelHashInsert(m.keys, m.hash_mask, VoxelHashKey(kx, ky, kz), nullptr)
-                          : (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
-    atomicAdd(m.count + c, 1);
-    double* s = m.sums + 9 * c;
-    atomicAdd(s + 0, x); atomicAdd(s + 1, y); atomicAdd(s + 2, z);
-    atomicAdd(s + 3, x * x); atomicAdd(s + 4, x * y); atomicAdd(s + 5, x * z);
-    atomicAdd(s + 6, y * y); atomicAdd(s + 7, y * z); atomicAdd(s + 8, z * z);
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together (the tail is masked), so that the shuffles below are converged
+  for (int64_t base = first - lane; base < m.n; base += stride) {
+    const int64_t i = base + lane;
+    const bool live = i < m.n;
+    int64_t c = -1;
+    long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+      const int ax = static_cast<int>(floor(m.xyz[3 * i] * m.inv_voxel));
+      const int ay = static_cast<int>(floor(m.xyz[3 * i + 1] * m.inv_voxel));
+      const int az = static_cast<int>(floor(m.xyz[3 * i + 2] * m.inv_voxel));
+      const double x = (m.xyz[3 * i] - (ax + 0.5) * m.voxel) * m.inv_voxel;
+      const double y = (m.xyz[3 * i + 1] - (ay + 0.5) * m.voxel) * m.inv_voxel;
+      const double z = (m.xyz[3 * i + 2] - (az + 0.5) * m.voxel) * m.inv_voxel;
+      const int kx = ax - m.kmin[0], ky = ay - m.kmin[1], kz = az - m.kmin[2];
+      c = m.keys != nullptr ? VoxelHashInsert(m.keys, m.hash_mask, VoxelHashKey(kx, ky, kz), nullptr)
+                            : (static_cast<int64_t>(kz) * m.dims[1] + ky) * m.dims[0] + kx;
+      const int sh = m.fixed_shift;
+      v[0] = ToFixed(x, sh); v[1] = ToFixed(y, sh); v[2] = ToFixed(z, sh);
+      v[3] = ToFixed(x * x, sh); v[4] = ToFixed(x * y, sh); v[5] = ToFixed(x * z, sh);
+      v[6] = ToFixed(y * y, sh); v[7] = ToFixed(y * z, sh); v[8] = ToFixed(z * z, sh);
+    }
+    const int64_t c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool uniform = __all_sync(0xffffffffu, c == c0 && live);
+    if (uniform) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+      if (lane == 0) {
+        atomicAdd(m.count + c, 32);
+        unsigned long long* s = reinterpret_cast<unsigned long long*>(m.sums) + 9 * c;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(s + k, static_cast<unsigned long long>(v[k]));
+      }
+    } else if (live) {
+      atomicAdd(m.count + c, 1);
+      unsigned long long* s = reinterpret_cast<unsigned long long*>(m.sums) + 9 * c;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(s + k, static_cast<unsigned long long>(v[k]));
+    }
   }
 }
 
@@ -1852,7 +2020,11 @@ __global__ void map_finalize_kernel(const MapAccumParams m, int64_t cells, int v
       idx[2] = c / (static_cast<int64_t>(m.dims[0]) * m.dims[1]);
     }
     const double inv_n = 1.0 / n;
-    const double* s = m.sums + 9 * c;
+    // fixed-point sums of d = (p - centre) / voxel and d d^T -> metres, metres^2
+    const long long* fixed = reinterpret_cast<const long long*>(m.sums) + 9 * c;
+    double s[9];
+    for (int k = 0; k < 9; ++k)
+      s[k] = scalbn(static_cast<double>(fixed[k]), -m.fixed_shift) * (k < 3 ? m.voxel : m.voxel * m.voxel);
     double off[3];  // mean relative to the voxel centre
     for (int a = 0; a < 3; ++a) {
       off[a] = s[a] * inv_n;

@@ -243,6 +243,11 @@ int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel
   ap.xyz = d_xyz; ap.n = n; ap.inv_voxel = inv; ap.voxel = voxel_size;
   for (int k = 0; k < 3; ++k) { ap.kmin[k] = kmin[k]; ap.dims[k] = dims[k]; }
   ap.count = d_count; ap.sums = d_sums;
+  {
+    int bits = 0;  // of the point count: |d| <= 1/2 summed n times must stay below 2^62
+    while ((static_cast<int64_t>(1) << bits) <= n) ++bits;
+    ap.fixed_shift = std::min(40, 61 - bits);
+  }
   ap.keys = m->d_keys; ap.hash_mask = m->hash_mask;
   if (e == cudaSuccess) e = LaunchMapAccumulate(ap, ctx->stream);
   if (e == cudaSuccess)
