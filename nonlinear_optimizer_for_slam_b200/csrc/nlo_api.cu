@@ -671,7 +671,7 @@ int nlo_context_create(int device, nlo_context** out) {
     return std::max(lo, std::min(hi, atoi(v)));
   };
   auto pow2_floor = [](int v) { int p2 = 1; while (2 * p2 <= v) p2 *= 2; return p2; };
-  ctx->cluster_small = pow2_floor(env_int("NLO_CLUSTER", 4, 1, kMaxCluster));
+  ctx->cluster_small = pow2_floor(env_int("NLO_CLUSTER", 8, 1, kMaxCluster));
   ctx->direct_max_clusters = env_int("NLO_DIRECT_MAX", 48, 0, 1 << 20);
   ctx->use_resident = env_int("NLO_NO_RESIDENT", 0, 0, 1) == 0;
   const char* tenv = getenv("NLO_INGEST_THREADS");

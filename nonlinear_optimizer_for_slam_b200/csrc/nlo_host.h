@@ -148,7 +148,7 @@ struct nlo_context {
   double l2_keep_mb = 0.0;        // NLO_L2_KEEP_MB: bytes of a re-read scan pinned in L2 (0 = off)
   double l2_policy_min_mb = 0.0;  // only scans larger than this get an explicit policy
   int grid_small = 0;             // CTAs of the persistent path for L2-resident problems
-  int cluster_small = 4;          // NLO_CLUSTER: CTAs per thread-block cluster, problems resident in smem / L2
+  int cluster_small = 8;          // NLO_CLUSTER: CTAs per thread-block cluster, problems resident in smem / L2
   int direct_max_clusters = 48;   // NLO_DIRECT_MAX: up to this many cluster partials every CTA gathers them itself
   bool use_resident = true;       // NLO_NO_RESIDENT=1: latency-bound registrations also run the streaming kernel
   int device_share = 1;           // sub-contexts of one multi-device context that sit on this device

@@ -156,14 +156,9 @@ struct ReduceArea {
 };
 
 // Shared memory of the resident kernel in front of its stages.
-constexpr int kStageRecords = 48;  // cluster partials a leader CTA gathers in one go (NLO_DIRECT_MAX <= this)
 struct ResidentSmem {
   ReduceArea red;
-  double stage[kStageRecords][kAcc6];  // gathered cluster partials, before they are added in fixed order
-  // LL words exchanged inside a thread-block cluster through distributed shared memory, by
-  // iteration parity: the sums of the cluster's CTAs (rank-0 CTA only) and the totals rank 0 returns
-  unsigned long long cl_in[2][kMaxCluster][kAcc6][2];
-  unsigned long long cl_out[2][kAcc6][2];
+  double cluster_part[2][kMaxCluster][kAcc6];  // rank-0 CTA of a cluster: the sums of its CTAs (by iteration parity)
   uint64_t full;  // all tiles of this CTA have landed
 };
 
@@ -221,23 +216,10 @@ __device__ __forceinline__ void StoreClusterF64(double* local, unsigned int targ
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(SmemAddr(local)), "r"(target_rank));
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
 }
-
-// LL words in (distributed) shared memory: the two 8-byte words of a double, each carrying the tag.
-// The writer stores into the copy of `local` that CTA `target_rank` of the cluster holds; the
-// reader polls its own shared memory -- no hardware barrier, no L2.
-__device__ __forceinline__ void StoreClusterLL(unsigned long long* local, unsigned int target_rank, double v,
-                                               unsigned int tag) {
-  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
-  const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
+__device__ __forceinline__ void StoreClusterU32(int* local, unsigned int target_rank, unsigned int v) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(SmemAddr(local)), "r"(target_rank));
-  asm volatile("st.relaxed.cluster.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(remote), "l"(t | (bits & 0xffffffffULL)),
-               "l"(t | (bits >> 32))
-               : "memory");
-}
-__device__ __forceinline__ void LoadSharedLL(const unsigned long long* local, unsigned long long& lo,
-                                             unsigned long long& hi) {
-  asm volatile("ld.relaxed.cluster.shared::cta.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(SmemAddr(local)) : "memory");
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------ "LL" words
@@ -323,58 +305,6 @@ __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride
   }
 }
 
-// The same sum for up to kStageRecords records with every load in flight at once: thread t takes one
-// (record, four consecutive values) item -- 33 records x 7 quads are 231 of the 256 threads -- polls
-// its four words until they carry the tag and parks the doubles in `stage`; the additions then run
-// over shared memory in exactly the order of GatherLL (records l8, l8+8, ... per lane, lanes in
-// order), so both give the same bits.  One L2 round trip after the last record lands instead of
-// one per record of a lane.
-template <int NACC>
-__device__ __noinline__ void GatherStaged(const unsigned long long* base, int stride_words, int n_src,
-                                          unsigned int tag, unsigned long long timeout_ns, double (*stage)[kAcc6],
-                                          double (*lanes)[kAcc6], double* total, int* fail) {
-  constexpr int kQuads = (NACC + 3) / 4;
-  const int tid = threadIdx.x;
-  SpinWatch watch;
-#pragma unroll 1
-  for (int item = tid; item < n_src * kQuads; item += kThreads) {
-    const int c = item / kQuads, j0 = 4 * (item - c * kQuads);
-    const unsigned long long* src = base + static_cast<size_t>(c) * stride_words + 2 * j0;
-    unsigned long long lo[4], hi[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (j0 + k < NACC) LoadLL(src + 2 * k, lo[k], hi[k], false);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (j0 + k < NACC) {
-        while (static_cast<unsigned int>(lo[k] >> 32) != tag || static_cast<unsigned int>(hi[k] >> 32) != tag) {
-          if (watch.Expired(timeout_ns)) {
-            *fail = 1;
-            lo[k] = hi[k] = static_cast<unsigned long long>(tag) << 32;
-            break;
-          }
-          LoadLL(src + 2 * k, lo[k], hi[k], false);
-        }
-        stage[c][j0 + k] = __longlong_as_double(static_cast<long long>((hi[k] << 32) | (lo[k] & 0xffffffffULL)));
-      }
-    }
-  }
-  __syncthreads();
-  const int j = tid >> 3, l8 = tid & 7;
-  if (j < NACC) {
-    double s = 0.0;
-    for (int c = l8; c < n_src; c += 8) s += stage[c][j];
-    lanes[l8][j] = s;
-  }
-  __syncthreads();
-  if (tid < NACC) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += lanes[w][tid];
-    total[tid] = s;
-  }
-}
-
 // profiling aid (NLO_DEBUG_TIMES=1): CTA 0 / thread 0 stamps the phases of each iteration
 // (NLO_DEBUG_TIMES=2: every CTA of the first registration, rows [CTA][iteration][8])
 #define NLO_STAMP(slot)                                                                         \
@@ -390,27 +320,25 @@ enum ReduceOutcome : int {
 };
 
 // Everything between the tile loop and the damped step of iteration `it` in the resident kernel.
-//  1. CTA sum (fixed order over the 8 warps).  The CTAs of a thread-block cluster hand their 28 sums
-//     to the cluster's rank-0 CTA as LL words in ITS shared memory (distributed shared memory: 32
-//     payload bits + the tag of this iteration per 8-byte store, valid the moment the tag matches);
-//     rank 0 polls its own shared memory, adds them in rank order and stores the cluster's partial,
-//     LL words again, to global memory.  No hardware barrier, no counter, no fence.
+//  1. CTA sum (fixed order over the 8 warps); the CTAs of a thread-block cluster hand their 28
+//     sums to the cluster's rank-0 CTA through distributed shared memory and meet at the hardware
+//     cluster barrier; rank 0 adds them in rank order and stores the cluster's partial as "LL"
+//     words (32 payload bits + the tag of this iteration per 8-byte store: a word is valid the
+//     moment its tag matches -- no counter, no fence).
 //  2. Only the rank-0 CTAs poll global memory.  gather_direct (few clusters): every rank-0 CTA
 //     gathers all cluster partials and adds them in cluster order.  Otherwise CTA 0 gathers,
 //     rotates to the canonical frame and stores the sums (LL again) into the local slot -- or,
 //     sharded across GPUs, into the slot of every rank over NVLink -- and the rank-0 CTAs gather
 //     those (in rank order: bit-identical sums, and therefore steps, on every GPU).
-//  3. Rank 0 hands the totals to the other CTAs of its cluster the same way (LL words into their
-//     shared memory), which they poll locally: 132 CTAs polling the same few L2 lines would
-//     serialise in the L2 slices and delay the very stores they wait for.
+//  3. Rank 0 hands the totals to the other CTAs of its cluster over distributed shared memory, second
+//     cluster barrier; the other CTAs sleep in that hardware barrier meanwhile instead of polling:
+//     132 CTAs polling the same few L2 lines serialise in the L2 slices and delay the very stores
+//     they wait for (measured: 2.7 us for the all-CTAs gather of 33 partials).
 //  4. Every CTA rotates to the canonical frame (if step 2 did not) and steps its own copy of the state.
-// A wait that expires is flagged in red.fail and travels to the cluster as a tag with bit 31 set.
-constexpr unsigned int kFailTagBit = 0x80000000u;
-
 template <int KIND>
 __device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterParams& p, const CanonPlan& plan, int it) {
-  constexpr int NACC = KindTraits<KIND>::kAcc;
   ReduceArea& red = sm.red;
+  constexpr int NACC = KindTraits<KIND>::kAcc;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int problem = blockIdx.y;
@@ -427,47 +355,29 @@ __device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterPar
   const unsigned int csize = ClusterSize(), crank = ClusterCtaRank();
   const bool leader = crank == 0;
   const bool grid_exchange = grid_x > 1 && !p.gather_direct;  // CTA 0 gathers on behalf of the grid
-  const int parity = it & 1;
-  const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;  // bit 31 clear
   bool canonical_done = false;
   if (grid_x == 1) {
     if (tid < NACC) red.total[tid] = cta_sum;
     NLO_STAMP(3);
   } else {
     const int n_clusters = static_cast<int>(ClusterCountX()), cluster_id = static_cast<int>(ClusterIdX());
+    const int parity = it & 1;
+    const unsigned int tag = p.tag_base + static_cast<unsigned int>(it) + 1u;
     unsigned long long* row_partials =
         p.ll_partials + static_cast<size_t>(parity * gridDim.y + problem) * n_clusters * (2 * NACC);
-    if (csize > 1 && tid < NACC) {
-      if (!leader) {
-        StoreClusterLL(&sm.cl_in[parity][crank][tid][0], 0u, cta_sum, tag);
-      } else {
-        SpinWatch watch;
-        for (unsigned int r = 1; r < csize; ++r) {  // rank order
-          unsigned long long lo, hi;
-          LoadSharedLL(&sm.cl_in[parity][r][tid][0], lo, hi);
-          while (static_cast<unsigned int>(lo >> 32) != tag || static_cast<unsigned int>(hi >> 32) != tag) {
-            if (watch.Expired(kGridTimeoutNs)) {
-              red.fail = 1;
-              lo = hi = 0ULL;
-              break;
-            }
-            LoadSharedLL(&sm.cl_in[parity][r][tid][0], lo, hi);
-          }
-          cta_sum += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
-        }
+    if (csize > 1) {
+      if (tid < NACC) StoreClusterF64(&sm.cluster_part[parity][crank][tid], 0u, cta_sum);
+      ClusterSync();
+      if (leader && tid < NACC) {
+        cta_sum = 0.0;
+        for (unsigned int r = 0; r < csize; ++r) cta_sum += sm.cluster_part[parity][r][tid];
       }
     }
     if (leader && tid < NACC)
       StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag, false);
     NLO_STAMP(3);
-    if (grid_exchange ? blockIdx.x == 0 : leader) {
-      if (n_clusters <= kStageRecords)
-        GatherStaged<NACC>(row_partials, 2 * NACC, n_clusters, tag, kGridTimeoutNs, sm.stage, red.gather_lanes,
-                           red.total, &red.fail);
-      else
-        GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, false, kGridTimeoutNs, red.gather_lanes, red.total,
-                       &red.fail);
-    }
+    if (grid_exchange ? blockIdx.x == 0 : leader)
+      GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, false, kGridTimeoutNs, red.gather_lanes, red.total, &red.fail);
   }
   NLO_STAMP(4);
   // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs, through the
@@ -492,9 +402,9 @@ __device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterPar
         for (int r = 0; r < nsrc; ++r) StoreLL(p.peer.slots[r] + slot, red.total[tid], xtag, true);
       }
     } else {
-      xtag = tag;
+      xtag = p.tag_base + static_cast<unsigned int>(it) + 1u;
       nsrc = 1;
-      unsigned long long* slot = p.ll_sums + (static_cast<size_t>(problem) * 2 + parity) * kPeerWords;
+      unsigned long long* slot = p.ll_sums + (static_cast<size_t>(problem) * 2 + (it & 1)) * kPeerWords;
       src = slot;
       if (pusher && tid < NACC) StoreLL(slot + 2 * tid, red.total[tid], xtag, false);
     }
@@ -509,34 +419,19 @@ __device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterPar
     }
   }
   if (csize > 1) {
-    if (leader) {
-      __syncthreads();  // red.fail of every thread is in
-      if (tid < NACC) {  // rank 0 -> the other CTAs of the cluster: the totals (red.total[tid] is this thread's)
-        const unsigned int out_tag = red.fail ? (tag | kFailTagBit) : tag;
-        const double v = red.total[tid];
-        for (unsigned int r = 1; r < csize; ++r) StoreClusterLL(&sm.cl_out[parity][tid][0], r, v, out_tag);
-      }
-    } else if (tid < NACC) {
-      SpinWatch watch;
-      unsigned long long lo, hi;
-      LoadSharedLL(&sm.cl_out[parity][tid][0], lo, hi);
-      while ((static_cast<unsigned int>(lo >> 32) & ~kFailTagBit) != tag ||
-             (static_cast<unsigned int>(hi >> 32) & ~kFailTagBit) != tag) {
-        if (watch.Expired(kGridTimeoutNs)) {
-          lo = hi = static_cast<unsigned long long>(kFailTagBit) << 32;
-          break;
-        }
-        LoadSharedLL(&sm.cl_out[parity][tid][0], lo, hi);
-      }
-      if ((lo >> 32) & kFailTagBit) red.fail = 1;
-      red.total[tid] = __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
+    // rank 0 -> the other CTAs of the cluster: the totals (and whether a wait expired)
+    if (leader && tid < NACC) {
+      const double v = red.total[tid];  // written by this thread
+      for (unsigned int r = 1; r < csize; ++r) StoreClusterF64(&red.total[tid], r, v);
     }
+    if (leader && tid == 0 && red.fail)
+      for (unsigned int r = 1; r < csize; ++r) StoreClusterU32(&red.fail, r, 1u);
+    ClusterSync();
   }
   NLO_STAMP(9);
   if (!canonical_done && KIND != kNdt3 && warp == 0)
     CanonicalRotate(red.total, st.R, &red.gather_lanes[0][0], plan, lane);
   NLO_STAMP(10);
-  if (csize > 1 && !leader) __syncthreads();  // red.fail set by warp 0 of a non-leader CTA
   return red.fail ? kReduceFailed : kReduceStep;
 }
 
@@ -572,9 +467,10 @@ __device__ __forceinline__ void StepPhase(ReduceArea& red, const IterParams& p, 
 template <int KIND>
 __device__ __forceinline__ int PostTileBody(ResidentSmem& sm, const IterParams& p, const CanonPlan& plan,
                                             State* st_global, int it) {
+  ReduceArea& red = sm.red;
   const int outcome = ReduceAndExchange<KIND>(sm, p, plan, it);
   NLO_STAMP(11);
-  if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(sm.red, p, st_global, it);
+  if (outcome == kReduceStep && threadIdx.x < 32) StepPhase<KIND>(red, p, st_global, it);
   return outcome;
 }
 // ------------------------------------------------------------------ streaming kernel
@@ -1036,11 +932,8 @@ __global__ void __launch_bounds__(kThreads, 1) gn_resident_kernel(const __grid_c
       }
     }
   }
-  // no stale word of the cluster exchange may carry a valid tag; and no CTA may store into the
-  // shared memory of a cluster peer that has not started yet
-  for (int k = tid; k < 2 * kMaxCluster * kAcc6 * 2; k += kThreads) (&sm.cl_in[0][0][0][0])[k] = 0ULL;
-  for (int k = tid; k < 2 * kAcc6 * 2; k += kThreads) (&sm.cl_out[0][0][0])[k] = 0ULL;
   __syncthreads();
+  // no CTA may store into the shared memory of a cluster peer that has not started yet
   if (ClusterSize() > 1) ClusterSync();
   if (my_tiles > 0) MbarWait(&sm.full, 0);
 
