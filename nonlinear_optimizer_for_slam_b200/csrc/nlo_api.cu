@@ -568,15 +568,19 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
   if (ctx->d_debug_times != nullptr && options->max_iterations >= 8 && options->max_iterations <= kDebugIterations) {
     std::vector<unsigned long long> ts(kDebugIterations * kDebugSlots);
     cudaMemcpy(ts.data(), ctx->d_debug_times, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    // average phase durations over iterations 2..7 (ns), CTA 0: tiles | CTA sync | cluster pre-reduction + LL store |
-    // gather of the cluster partials | canonical + [exchange] + step | CTA sync
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    double period = 0;
-    for (int it = 2; it < 8; ++it) {
-      for (int k = 0; k < 6; ++k)
-        acc[k] += static_cast<double>(ts[it * kDebugSlots + k + 1]) - static_cast<double>(ts[it * kDebugSlots + k]);
-      period += static_cast<double>(ts[(it + 1) * kDebugSlots]) - static_cast<double>(ts[it * kDebugSlots]);
-    }
+    // Phase stamps of CTA 0, averaged over iterations 2..7 (ns).  Stamps 0-6: iteration start, tiles done,
+    // CTA sync, [resident: cluster pre-reduction + LL store | streaming: all CTAs arrived], sums gathered,
+    // stepped, CTA sync; 8-14 (resident kernel only): sub-phases.  A stamp a launch shape does not take is 0.
+    auto span = [&](int from, int to, double* out) {
+      double total = 0.0;
+      for (int it = 2; it < 8; ++it) {
+        const unsigned long long a0 = ts[it * kDebugSlots + from], a1 = ts[it * kDebugSlots + to];
+        if (a0 == 0ULL || a1 == 0ULL) return false;
+        total += static_cast<double>(a1) - static_cast<double>(a0);
+      }
+      *out = total / 6.0;
+      return true;
+    };
     if (ctx->debug_all_ctas && getenv("NLO_DEBUG_FILE") != nullptr) {
       std::vector<unsigned long long> all(static_cast<size_t>(kDebugCtas) * kDebugIterations * kDebugSlots);
       cudaMemcpy(all.data(), ctx->d_debug_times, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -584,19 +588,43 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
         fwrite(all.data(), sizeof(unsigned long long), all.size(), f);
         fclose(f);
       }
-      cudaMemset(ctx->d_debug_times, 0, all.size() * sizeof(unsigned long long));
     }
+    std::string line = "[nlo debug] ns/iter:";
+    const char* names[6] = {"tiles", "cta-sync", "pre-reduce|arrivals", "gather", "canon+xchg+step", "sync"};
+    char buf[96];
+    for (int k = 0; k < 6; ++k) {
+      double v = 0.0;
+      // a missing stamp 3 (single-CTA loop) folds phases 2 and 3 into one
+      const bool ok = span(k, k + 1, &v);
+      if (ok) snprintf(buf, sizeof(buf), " %s %.0f |", names[k], v);
+      else snprintf(buf, sizeof(buf), " %s - |", names[k]);
+      line += buf;
+    }
+    double period = 0.0;
     {
-      // sub-phases relative to stamp 2 (the CTA sync after the tiles)
-      double sub[7] = {0, 0, 0, 0, 0, 0, 0};
+      double total = 0.0;
       for (int it = 2; it < 8; ++it)
-        for (int k = 0; k < 7; ++k)
-          sub[k] += static_cast<double>(ts[it * kDebugSlots + 8 + k]) - static_cast<double>(ts[it * kDebugSlots + 2]);
-      fprintf(stderr, "[nlo debug] ns after cta-sync: reduce-entry %.0f | (9) %.0f | canonical-done %.0f | reduce-returned %.0f | step-entry %.0f | stepped %.0f | state-out %.0f\n",
-              sub[0] / 6, sub[1] / 6, sub[2] / 6, sub[3] / 6, sub[4] / 6, sub[5] / 6, sub[6] / 6);
+        total += static_cast<double>(ts[(it + 1) * kDebugSlots]) - static_cast<double>(ts[it * kDebugSlots]);
+      period = total / 6.0;
     }
-    fprintf(stderr, "[nlo debug] ns/iter: tiles %.0f | cta-sync %.0f | cluster+ll %.0f | gather %.0f | canon+xchg+step %.0f | sync %.0f | period %.0f\n",
-            acc[0] / 6, acc[1] / 6, acc[2] / 6, acc[3] / 6, acc[4] / 6, acc[5] / 6, period / 6);
+    snprintf(buf, sizeof(buf), " period %.0f", period);
+    line += buf;
+    fprintf(stderr, "%s\n", line.c_str());
+    double sub = 0.0;
+    if (span(2, 8, &sub)) {  // resident kernel: sub-phases after the CTA sync
+      const char* sub_names[7] = {"reduce-entry", "totals-in-cluster", "canonical", "reduce-returned", "step-entry",
+                                  "stepped", "state-out"};
+      std::string sline = "[nlo debug] ns after cta-sync:";
+      for (int k = 0; k < 7; ++k) {
+        double v = 0.0;
+        if (span(2, 8 + k, &v)) {
+          snprintf(buf, sizeof(buf), " %s %.0f |", sub_names[k], v);
+          sline += buf;
+        }
+      }
+      fprintf(stderr, "%s\n", sline.c_str());
+    }
+    cudaMemset(ctx->d_debug_times, 0, static_cast<size_t>(kDebugCtas) * kDebugIterations * kDebugSlots * sizeof(unsigned long long));
   }
   int rc_all = NLO_OK;
   for (int k = 0; k < B; ++k) {

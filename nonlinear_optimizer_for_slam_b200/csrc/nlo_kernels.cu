@@ -576,7 +576,10 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   const Range range = p.ranges[problem];
   const int64_t tile_lo = range.begin / kTile;
   const int64_t tile_hi = (range.end + kTile - 1) / kTile;
-  // tiles of this CTA: tile_lo + blockIdx.x + m * grid_x
+  // tiles of this CTA: tile_lo + blockIdx.x + m * grid_x.  (Static, so that the sums are reproducible.
+  // A biased split between the two CTAs of an SM -- the younger one finishes 5 - 8 us later in every
+  // iteration of an 8 M-point shard -- was tried and is slower: the SM's bandwidth is shared, the
+  // SM is done when both are, 51.6 / 48.4 costs 2 %.)
   const int64_t span = tile_hi - tile_lo;
   const int my_tiles =
       (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
@@ -615,11 +618,12 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
           // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy.
           // l2_keep_tiles > 0: the scan is re-read every iteration and is larger than what the L2
-          // keeps by itself -- pin the first tiles (evict_last), stream the rest (evict_first).
+          // keeps by itself -- pin the first tiles of every CTA (evict_last, l2_keep_tiles in all),
+          // stream the rest (evict_first).
           const ST* src = reinterpret_cast<const ST*>(p.planes[0]) + tile * (NPLANES * kTile);
           if (p.l2_keep_tiles > 0)
             BulkLoadHint(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s],
-                         (tile - tile_lo) < p.l2_keep_tiles ? policy_keep : policy_stream);
+                         static_cast<long long>(m) * grid_x < p.l2_keep_tiles ? policy_keep : policy_stream);
           else
             BulkLoad(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s]);
         };
