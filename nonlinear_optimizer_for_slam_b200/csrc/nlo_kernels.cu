@@ -1,22 +1,27 @@
 // nlo_kernels.cu -- sm_100a kernels of the hot path.
 //
-// gn_iteration_kernel<KIND, LOSS>: the device-resident Gauss-Newton / damped-LM loop (or a single
-// iteration of it) of one or many registrations:
+// The device-resident Gauss-Newton / damped-LM loop (or a single iteration of it) of one or many
+// registrations, as two kernels:
 //
-//   HBM tiles (tile-interleaved SoA, one contiguous 30 KB run per 256 correspondences)
+// gn_iteration_kernel<KIND, LOSS, ST> -- the STREAMING kernel (scans that do not fit shared memory)
+//   HBM tiles (tile-interleaved SoA, one contiguous 24 KB run per 256 correspondences)
 //     --cp.async.bulk (TMA 1-D, one copy per tile, L2 eviction hint), mbarrier full/empty ring-->
-//   shared-memory stages (resident across iterations when the CTA's share fits the ring)
+//   shared-memory stages
 //     --> 8 warps: residual, analytic Jacobian terms, device-inlined robust loss, 28 (10) fp64
 //         register accumulators per thread
-//     --> recursive-halving warp reduction -> shared -> per-CTA partial (HBM/L2)
+//     --> recursive-halving warp reduction -> shared -> per-CTA partial (HBM/L2) + arrival counter
 //     --> leader CTA: fixed-order fp64 sum of the partials, rotation to the canonical H|g,
 //         [LL-format peer-memory all-reduce over NVLink when the scan is sharded across GPUs],
 //         damped 6x6 LDL^T / 3x3 solve, pose update, convergence tests, lambda schedule, trace row
-//     --> new state published to the other CTAs (persistent grid) or left in HBM (next launch).
+//     --> new state published to the other CTAs as LL words (persistent grid) or left in HBM.
+//   Launch shapes (chosen in nlo_api.cu): persistent cooperative grid with the whole loop inside,
+//   one CTA per registration with the whole loop inside (batched), or one launch per iteration
+//   with a last-CTA-by-ticket finaliser (NCCL flavour, plain assemble calls).
 //
-// Launch shapes (chosen in nlo_api.cu): persistent cooperative grid with the whole loop inside,
-// one CTA per registration with the whole loop inside (batched), or one launch per iteration
-// with a last-CTA-by-ticket finaliser (NCCL flavour, plain assemble calls).
+// gn_resident_kernel<KIND, LOSS> -- the RESIDENT kernel (latency-bound registrations: every tile is
+//   loaded into shared memory once per Solve).  One CTA per SM, thread-block clusters: the CTAs of a
+//   cluster pre-reduce over distributed shared memory, the cluster leaders exchange LL-format
+//   partials through L2 and hand the totals back over DSMEM, every CTA performs the identical step.
 //
 // Replaces the per-iteration loops of (paths relative to /root/reference/nonlinear_optimizer/)
 //   mahalanobis_distance_minimizer/mahalanobis_distance_minimizer_analytic.cc:92-149
