@@ -158,6 +158,47 @@ def test_ndt3_solve_trajectory(ctx, nlo, oracle, n, loss):
     prob.close()
 
 
+# Launch-shape boundaries of the device-resident loop (nlo_api.cu::EnqueueLoop): <= 3 tiles run inside one
+# CTA; up to 8 tiles per CTA of one CTA per SM run in the resident kernel (clusters of 8 CTAs: partly
+# idle clusters at 4 - 9 tiles, an odd tile count per CTA pairs the last tile with a masked one, the
+# last size that fits is ~132 x 8 tiles); anything larger streams.
+@pytest.mark.parametrize("n", [769, 1025, 2049, 2305, 33793, 68000, 270000, 271000, 303105])
+def test_ndt6_solve_trajectory_at_the_launch_shape_boundaries(ctx, nlo, oracle, n):
+    point, mean, S = (a[:n] for a in syn.ndt_problem(n + n // 8 + 64, 1007, syn.CFG1_TRUE))
+    assert len(point) == n   # the exact tile count matters here
+    prob = nlo.NdtProblem(ctx, capacity=len(point))
+    prob.upload(point, mean, S)
+    ctx.set_loss(1, [1.0, 1.0])
+    opts = nlo.Options(max_iterations=12)
+    res = prob.solve6(nlo.identity_pose(), opts, trace=True)
+    ref = oracle.ndt6_solve(point, mean, S, nlo.identity_pose(), 1, [1.0, 1.0], max_iterations=12)
+    _check_trajectory(res, ref, 36, nlo)
+    again = prob.solve6(nlo.identity_pose(), opts, trace=True)   # bitwise repeatable in every shape
+    assert np.array_equal(res["trace"], again["trace"]) and np.array_equal(res["pose"], again["pose"])
+    prob.close()
+
+
+@pytest.mark.parametrize("n", [1025, 9000, 200001, 800000])
+def test_planar_and_reprojection_at_the_launch_shape_boundaries(ctx, nlo, oracle, n):
+    point, mean, S = syn.ndt_problem(min(n, 300000), 1008, syn.CFG2_TRUE)
+    prob = nlo.NdtProblem(ctx, capacity=len(point))
+    prob.upload(point, mean, S)
+    ctx.set_loss(2, [1.0])
+    opts = nlo.Options(max_iterations=10)
+    res = prob.solve3(nlo.identity_pose(), opts, trace=True)
+    ref = oracle.ndt3_solve(point, mean, S, nlo.identity_pose(), 2, [1.0], max_iterations=10)
+    _check_trajectory(res, ref, 17, nlo, three_dof=True)
+    prob.close()
+    X, px, K = syn.pnp_problem(n, 1009)   # 800 000 is past what the resident kernel holds (10 KB tiles, 22 per CTA)
+    rp = nlo.ReprojProblem(ctx, capacity=len(X))
+    rp.upload(X, px, K)
+    ctx.set_loss(3, [1e-2])
+    res = rp.solve(nlo.identity_pose(), opts, trace=True)
+    ref = oracle.reproj_solve(X, px, K, nlo.identity_pose(), 3, [1e-2], max_iterations=10)
+    _check_trajectory(res, ref, 36, nlo)
+    rp.close()
+
+
 def test_reproj_solve_cauchy(ctx, nlo, oracle):
     X, px, K = syn.pnp_problem(50000, 1003)
     prob = nlo.ReprojProblem(ctx, capacity=len(X))
