@@ -9,6 +9,9 @@
 // dispatcher in nlo_multi.cu.  No arithmetic of the hot path runs on the host and there is no CPU
 // fallback.
 #include <dlfcn.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <climits>
@@ -805,11 +808,63 @@ int nlo_set_loss(nlo_context* ctx, int kind, const double params[2]) {
   return NLO_OK;
 }
 
+// Pinned host memory ON THE NUMA NODE OF THE CURRENT DEVICE (best effort): anonymous pages bound to the
+// node of the GPU's PCIe root, touched, then registered with CUDA.  With several GPUs per box the
+// uploads of the GPUs on the second socket otherwise all cross the inter-socket link (a process
+// usually starts on the first socket and cudaMallocHost places the pages where the caller runs).
+namespace {
+std::mutex g_host_mu;
+std::map<void*, size_t> g_host_blocks;  // mmap'ed + registered blocks handed out by nlo_host_alloc
+}  // namespace
+
 int nlo_host_alloc(void** ptr, size_t bytes) {
   if (ptr == nullptr) return NLO_EINVAL;
-  return cudaMallocHost(ptr, bytes) == cudaSuccess ? NLO_OK : NLO_ENOMEM;
+  *ptr = nullptr;
+  if (bytes == 0) return NLO_EINVAL;
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) {
+    cudaGetLastError();
+    return NLO_ECUDA;
+  }
+  const size_t page = 1u << 21;
+  const size_t len = ((bytes + page - 1) / page) * page;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return NLO_ENOMEM;
+#ifdef SYS_mbind
+  const int node = DeviceNumaNode(device);
+  if (node >= 0 && node < 64) {
+    unsigned long mask = 1ul << node;
+    syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u);  // refused (cpuset) = default placement
+  }
+#endif
+  madvise(p, len, MADV_HUGEPAGE);
+  memset(p, 0, len);  // first touch under the policy
+  if (cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    munmap(p, len);
+    return NLO_ENOMEM;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_host_blocks[p] = len;
+  }
+  *ptr = p;
+  return NLO_OK;
 }
-int nlo_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NLO_OK : NLO_ECUDA; }
+int nlo_host_free(void* ptr) {
+  if (ptr == nullptr) return NLO_OK;
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    auto it = g_host_blocks.find(ptr);
+    if (it == g_host_blocks.end()) return NLO_EINVAL;
+    len = it->second;
+    g_host_blocks.erase(it);
+  }
+  const bool ok = cudaHostUnregister(ptr) == cudaSuccess;
+  munmap(ptr, len);
+  return ok ? NLO_OK : NLO_ECUDA;
+}
 
 // ---- problems ----
 static int CreateAny(nlo_context* ctx, int family, int num_problems, const int64_t* counts, bool batched, bool f32,

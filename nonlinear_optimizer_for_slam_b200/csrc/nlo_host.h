@@ -269,6 +269,7 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
               nlo_solve_result* results, double* trace, bool batched_call);
 
 // nlo_ingest.cu
+int DeviceNumaNode(int device);  // NUMA node of the device's PCIe root, -1 if unknown
 int UploadNdt(nlo_context* ctx, nlo_problem* pr, int64_t n, const double* point, const double* mean,
               const double* sqrt_info);
 int UploadNdtF32(nlo_context* ctx, nlo_problem* pr, int64_t n, const float* point, const float* mean,

@@ -41,6 +41,8 @@ struct Segment {
   int64_t src_begin, dst_begin, count;
 };
 
+}  // namespace
+
 // ---- NUMA placement (best effort): pinned chunks and gather threads near the GPU's PCIe root ----
 int DeviceNumaNode(int device) {
   char bus[32] = {0};
@@ -54,6 +56,8 @@ int DeviceNumaNode(int device) {
   fclose(f);
   return node;
 }
+
+namespace {
 
 // CPUs of a NUMA node that this process may run on (empty if unknown).
 std::vector<int> NodeCpus(int node) {
