@@ -214,6 +214,22 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
       cudaGetLastError();  // not co-resident right now: fall through to one CTA per registration
     }
   }
+  if (in_cta_loop && !pr->batched && ctx->use_persistent && ctx->use_resident && tags_fit && !pr->f32) {
+    // a registration of <= 3 tiles: the resident kernel as a single CTA (its step and rotation are
+    // the fast, fully inlined ones; nothing is exchanged)
+    IterParams q = p;
+    q.mode = kModeSolve;
+    q.persistent = 1;
+    q.iterations_in_kernel = opt.max_iterations;
+    q.gather_direct = 1;
+    const int rc = NextEpoch(ctx, pr, &q.tag_base);
+    if (rc != NLO_OK) return rc;
+    const cudaError_t ce = LaunchResident(kind, ctx->loss_kind, q, 1, 1, 1, static_cast<int>(std::max<int64_t>(tiles, 1)), ctx->stream);
+    if (ce == cudaSuccess) return NLO_OK;
+    if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
+      return Fail(ctx, NLO_ECUDA, std::string("cooperative launch (resident, one CTA): ") + cudaGetErrorString(ce));
+    cudaGetLastError();
+  }
   if (in_cta_loop) {
     // whole loop inside one CTA per registration: a single launch
     p.mode = kModeSolve;

@@ -378,11 +378,18 @@ __device__ __forceinline__ int ReduceAndExchange(ResidentSmem& sm, const IterPar
         for (unsigned int r = 0; r < csize; ++r) cta_sum += sm.cluster_part[parity][r][tid];
       }
     }
-    if (leader && tid < NACC)
-      StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag, false);
-    NLO_STAMP(3);
-    if (grid_exchange ? blockIdx.x == 0 : leader)
-      GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, false, kGridTimeoutNs, red.gather_lanes, red.total, &red.fail);
+    if (n_clusters == 1) {
+      // one cluster holds the whole registration: its rank-0 CTA already has the sums, nothing goes through L2
+      if (leader && tid < NACC) red.total[tid] = cta_sum;
+      NLO_STAMP(3);
+    } else {
+      if (leader && tid < NACC)
+        StoreLL(row_partials + static_cast<size_t>(cluster_id) * (2 * NACC) + 2 * tid, cta_sum, tag, false);
+      NLO_STAMP(3);
+      if (grid_exchange ? blockIdx.x == 0 : leader)
+        GatherLL<NACC>(row_partials, 2 * NACC, n_clusters, tag, false, kGridTimeoutNs, red.gather_lanes, red.total,
+                       &red.fail);
+    }
   }
   NLO_STAMP(4);
   // Exchange of the canonical sums: over NVLink when the scan is sharded across GPUs, through the
