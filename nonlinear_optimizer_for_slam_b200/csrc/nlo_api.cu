@@ -264,6 +264,14 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     int gx = grid_x;
     if (tiles < 4LL * ctx->grid_single)
       gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, ctx->grid_small)));
+    // One 512-thread CTA per SM with two tiles per ring stage instead of two 256-thread CTAs (see the
+    // kernel): a single tile stream per SM, half the partials.  fp64 storage only.
+    int wg = 1;
+    if (ctx->warp_groups == 2 && !pr->f32 && tiles >= 2 && (kind == kNdt3 || ctx->warp_groups_all)) {
+      wg = 2;
+      const int64_t stages_total = (tiles + 1) / 2;
+      gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(stages_total, ctx->grid_small)));
+    }
     p.mode = kModeSolve;
     p.persistent = 1;
     p.iterations_in_kernel = opt.max_iterations;
@@ -278,7 +286,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
         p.l2_keep_tiles = static_cast<long long>(ctx->l2_keep_mb / tile_mb);
     }
     NLO_CUDA(ctx, cudaMemsetAsync(pr->d_sync, 0, kSyncStride * sizeof(unsigned long long), ctx->stream));
-    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, 1, ctx->stream);
+    const cudaError_t ce = LaunchIteration(kind, ctx->loss_kind, p, gx, 1, 1, ctx->stream, wg);
     if (ce == cudaSuccess) return NLO_OK;
     if (ce != cudaErrorCooperativeLaunchTooLarge && ce != cudaErrorLaunchOutOfResources)
       return Fail(ctx, NLO_ECUDA, std::string("cooperative launch: ") + cudaGetErrorString(ce));
@@ -721,6 +729,11 @@ int nlo_context_create(int device, nlo_context** out) {
   ctx->cluster_small = pow2_floor(env_int("NLO_CLUSTER", 8, 1, kMaxCluster));
   ctx->direct_max_clusters = env_int("NLO_DIRECT_MAX", 48, 0, 1 << 20);
   ctx->use_resident = env_int("NLO_NO_RESIDENT", 0, 0, 1) == 0;
+  ctx->warp_groups = env_int("NLO_WARP_GROUPS", 2, 1, 2);
+  // Used for the planar kind only (10 accumulators): 1 - 3 % faster at every streamed size.  The 28
+  // accumulators of the 6-DoF kinds leave no register for the second warp group's indexing: ndt6 spills
+  // ~100 bytes into the tile loop and loses 14 %, PnP loses 6 %.  NLO_WARP_GROUPS_ALL=1 forces it anyway.
+  ctx->warp_groups_all = env_int("NLO_WARP_GROUPS_ALL", 0, 0, 1) != 0;
   const char* tenv = getenv("NLO_INGEST_THREADS");
   if (tenv != nullptr) ctx->ingest_threads = atoi(tenv);
   const char* denv = getenv("NLO_DEBUG_TIMES");

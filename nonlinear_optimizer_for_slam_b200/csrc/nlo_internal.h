@@ -115,8 +115,9 @@ struct IterParams {
 
 // Launchers (nlo_kernels.cu).  grid_x CTAs per registration, num_problems registrations.
 // `cluster` CTAs per thread-block cluster (1 = none; grid_x must be a multiple of it).
+// warp_groups: 1 = 256 threads, one tile per ring stage (2 CTAs/SM); 2 = 512 threads, two tiles per stage (1 CTA/SM).
 cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
-                            int cluster, cudaStream_t stream);
+                            int cluster, cudaStream_t stream, int warp_groups = 1);
 int MaxCoResidentCtas(int kind, int loss, bool f32, int cluster, bool resident);
 // Resident kernel: the whole registration lives in the shared memory of the grid, `stages` tiles per CTA
 // (<= ResidentMaxStages(kind)); always a persistent cooperative launch of the complete loop.

@@ -149,7 +149,7 @@ __host__ __device__ constexpr int PlanesOf() {
 
 // Shared memory of the reduction / exchange / step phase of an iteration (the same for every kind).
 struct ReduceArea {
-  double warp_sums[8][kAcc6];     // sums of the 8 consumer warps
+  double warp_sums[16][kAcc6];    // sums of the 8 (16) consumer warps
   double gather_lanes[8][kAcc6];  // the 8 strided lanes of a cross-CTA / cross-cluster / cross-rank sum
   double total[32];               // reduced (raw, then canonical) sums
   State state;                    // CTA-local copy of the registration state
@@ -169,7 +169,8 @@ struct ResidentSmem {
 
 // ST = storage type of the planes in HBM and in the stages: double (parity mode, 96 B per NDT
 // correspondence) or float (fp32 storage, fp64 math: 48 B; twice the stages fit the same smem).
-template <int KIND, typename ST>
+// WG = warp groups (of 8 warps) per CTA = consecutive tiles per ring stage, see the kernel.
+template <int KIND, typename ST, int WG = 1>
 struct SmemLayout {
   using T = KindTraits<KIND>;
   // bytes per stage: NDT fp64 24 KB (12 planes), NDT fp32 12 KB, PnP 10 KB; two CTAs per SM share
@@ -177,16 +178,17 @@ struct SmemLayout {
 #ifndef NLO_NDT_STAGES
 #define NLO_NDT_STAGES 4
 #endif
-  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? NLO_NDT_STAGES : 8);
-  ST stages[kStages][PlanesOf<KIND, ST>()][kTile];
+  // (WG = 2: three 48 KB stages -- the depth the streaming loop uses anyway -- leave the L1 ~90 KB instead of ~30)
+  static constexpr int kStages = (KIND == kReproj) ? 4 : (sizeof(ST) == 8 ? (WG == 2 ? 3 : NLO_NDT_STAGES) : 8);
+  ST stages[kStages][WG][PlanesOf<KIND, ST>()][kTile];
   ReduceArea red;
   uint64_t full[kStages];
   uint64_t empty[kStages];
 };
 
-template <int KIND, typename ST = double>
+template <int KIND, typename ST = double, int WG = 1>
 constexpr size_t SmemBytes() {
-  return sizeof(SmemLayout<KIND, ST>);
+  return sizeof(SmemLayout<KIND, ST, WG>);
 }
 
 // ------------------------------------------------------------------ thread-block cluster helpers
@@ -552,22 +554,33 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
 }
 
 
-template <int KIND, int LOSS, typename ST>
-__global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterParams p) {
+// WG = 1: 256 threads, two CTAs per SM, one 256-correspondence tile per ring stage.
+// WG = 2: 512 threads, ONE CTA per SM, two consecutive tiles (one contiguous 48 KB run) per stage, each
+//   of the two warp groups taking one of them.  Same warps, registers and bytes in flight per SM, but a
+//   single tile stream per SM: with two CTAs per SM the one placed second finishes its tiles 5 - 8 us
+//   after its older neighbour in EVERY iteration of an 8 M-point shard (12 us between the first and the
+//   last CTA of the grid; 3 us with one CTA per SM), and everybody waits for the last one.  It also
+//   halves the partials, arrivals and pollers of the exchange.  Used for the persistent loop of a
+//   streamed scan; batched registrations (tile-aligned, one CTA each) keep WG = 1.
+template <int KIND, int LOSS, typename ST, int WG>
+__global__ void __launch_bounds__(kThreads * WG, WG == 1 ? 2 : 1) gn_iteration_kernel(const IterParams p) {
   using T = KindTraits<KIND>;
   constexpr int NACC = T::kAcc;
   constexpr int NPLANES = PlanesOf<KIND, ST>();
-  constexpr int MAX_STAGES = SmemLayout<KIND, ST>::kStages;
+  constexpr int MAX_STAGES = SmemLayout<KIND, ST, WG>::kStages;
+  constexpr int kWarps = kConsumerWarps * WG;
   // ring depth actually used (<= the stages allocated): chosen per launch shape by the host
   const int STAGES = (p.stage_depth > 0 && p.stage_depth < MAX_STAGES) ? p.stage_depth : MAX_STAGES;
   constexpr uint32_t kStageBytes = NPLANES * kTile * sizeof(ST);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout<KIND, ST>& sm = *reinterpret_cast<SmemLayout<KIND, ST>*>(smem_raw);
+  SmemLayout<KIND, ST, WG>& sm = *reinterpret_cast<SmemLayout<KIND, ST, WG>*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  const int sub = (WG == 1) ? 0 : (tid >> 8);    // warp group = tile within a stage
+  const int elem = (WG == 1) ? tid : (tid & 255);  // correspondence within the tile
   const int problem = blockIdx.y;
   const int grid_x = gridDim.x;
   State* st_global = p.states + problem;
@@ -577,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
     if (p.mode != kModeStepOnly) {
       for (int s = 0; s < MAX_STAGES; ++s) {
         MbarInit(&sm.full[s], 1);
-        MbarInit(&sm.empty[s], kConsumerWarps);
+        MbarInit(&sm.empty[s], kWarps);
       }
       FenceBarrierInit();
     }
@@ -592,9 +605,15 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   // A biased split between the two CTAs of an SM -- the younger one finishes 5 - 8 us later in every
   // iteration of an 8 M-point shard -- was tried and is slower: the SM's bandwidth is shared, the
   // SM is done when both are, 51.6 / 48.4 costs 2 %.)
-  const int64_t span = tile_hi - tile_lo;
+  // (in units of stages: WG consecutive tiles; the last stage of a range may hold fewer).  Positions
+  // inside the range are 32-bit -- a problem holds < 2^31 correspondences -- which spares the tile
+  // loop a few registers.
+  const int span_tiles = static_cast<int>(tile_hi - tile_lo);
+  const int span = (span_tiles + WG - 1) / WG;
   const int my_tiles =
-      (span > blockIdx.x) ? static_cast<int>((span - blockIdx.x + grid_x - 1) / grid_x) : 0;
+      (span > static_cast<int>(blockIdx.x)) ? (span - static_cast<int>(blockIdx.x) + grid_x - 1) / grid_x : 0;
+  const int valid_lo = static_cast<int>(range.begin - tile_lo * kTile);  // first / one-past-last valid
+  const int valid_hi = static_cast<int>(range.end - tile_lo * kTile);    // correspondence, from tile_lo
   const bool writer = (blockIdx.x == 0) || !p.persistent;  // who publishes state / trace / sums
 
   const uint64_t policy_keep = PolicyEvictLast(), policy_stream = PolicyEvictFirst();
@@ -604,7 +623,8 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
   uint32_t c_phase = 0, p_phase = 0;
   // When the CTA's share of the scan fits the stage ring and the loop runs in-kernel, the tiles are
   // loaded once and stay resident in shared memory for every later iteration (no HBM/L2 re-read).
-  const bool resident = (p.iterations_in_kernel > 1) && (my_tiles <= STAGES);
+  // (never with WG = 2: registrations that small run the resident kernel)
+  const bool resident = (WG == 1) && (p.iterations_in_kernel > 1) && (my_tiles <= STAGES);
   // Streaming case: the first tiles of the NEXT iteration (the same tiles, they do not depend on
   // the pose) are requested before this iteration's reduction / step, which hides the pipeline
   // ramp behind the grid-wide exchange.  `prefetched` tiles of the coming iteration are in flight.
@@ -626,18 +646,21 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
           const uint32_t phase = p_phase;
           if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1u; }
           MbarWait(&sm.empty[s], phase ^ 1u);
-          MbarExpectTx(&sm.full[s], kStageBytes);
-          const int64_t tile = tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x;
+          const int first = (static_cast<int>(blockIdx.x) + m * grid_x) * WG;  // tiles before it in the range
+          const int64_t tile = tile_lo + first;
+          const uint32_t bytes =
+              (WG == 1 || span_tiles - first >= WG) ? kStageBytes * WG : kStageBytes * static_cast<uint32_t>(span_tiles - first);
+          MbarExpectTx(&sm.full[s], bytes);
           // one contiguous NP x 2 KB run per tile (tile-interleaved layout): a single bulk copy.
           // l2_keep_tiles > 0: the scan is re-read every iteration and is larger than what the L2
           // keeps by itself -- pin the first tiles of every CTA (evict_last, l2_keep_tiles in all),
           // stream the rest (evict_first).
           const ST* src = reinterpret_cast<const ST*>(p.planes[0]) + tile * (NPLANES * kTile);
           if (p.l2_keep_tiles > 0)
-            BulkLoadHint(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s],
-                         static_cast<long long>(m) * grid_x < p.l2_keep_tiles ? policy_keep : policy_stream);
+            BulkLoadHint(&sm.stages[s][0][0][0], src, bytes, &sm.full[s],
+                         static_cast<long long>(m) * grid_x * WG < p.l2_keep_tiles ? policy_keep : policy_stream);
           else
-            BulkLoad(&sm.stages[s][0][0], src, kStageBytes, &sm.full[s]);
+            BulkLoad(&sm.stages[s][0][0][0], src, bytes, &sm.full[s]);
         };
         const bool need_load = !resident || it == 0;
         if (tid == 0 && need_load) {
@@ -666,22 +689,28 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
             __syncwarp();
             MbarWait(&sm.full[s], phase);
           }
+          // this warp group's tile of the stage (the last stage of the range may not have one)
+          const int my_tile = (static_cast<int>(blockIdx.x) + m * grid_x) * WG + sub;
+          const bool have_tile = (WG == 1) || my_tile < span_tiles;
           double v[NPLANES];
+          if (have_tile) {
 #pragma unroll
-          for (int pl = 0; pl < NPLANES; ++pl) v[pl] = static_cast<double>(sm.stages[s][pl][tid]);
+            for (int pl = 0; pl < NPLANES; ++pl) v[pl] = static_cast<double>(sm.stages[s][sub][pl][elem]);
+          }
           if (!resident) {
             __syncwarp();
             if (lane == 0) MbarArrive(&sm.empty[s]);
           }
-          const int64_t idx =
-              (tile_lo + blockIdx.x + static_cast<int64_t>(m) * grid_x) * kTile + tid;
-          const bool valid = (idx >= range.begin) && (idx < range.end);
-          if (KIND == kNdt6)
-            Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
-          else if (KIND == kNdt3)
-            Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
-          else
-            ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
+          if (have_tile) {
+            const int idx = my_tile * kTile + elem;
+            const bool valid = (idx >= valid_lo) && (idx < valid_hi);
+            if (KIND == kNdt6)
+              Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            else if (KIND == kNdt3)
+              Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+            else
+              ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
+          }
         }
         // Warp reduction of the NACC accumulators by recursive halving: at offset 16 each lane
         // keeps half of the values and hands the other half to its partner, at offset 8 a
@@ -720,11 +749,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_iteration_kernel(const IterPar
       __syncthreads();
       NLO_STAMP(2);
 
-      // CTA sum over the 8 consumer warps, fixed order
+      // CTA sum over the consumer warps, fixed order
       if (tid < NACC) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += sm.red.warp_sums[w][tid];
+        for (int w = 0; w < kWarps; ++w) s += sm.red.warp_sums[w][tid];
         sm.red.total[tid] = s;
       }
       if (grid_x > 1) {
@@ -1061,36 +1090,39 @@ struct KernelEntry {
 };
 
 template <int KIND, int LOSS>
-static KernelEntry EntryOne(bool f32) {
+static KernelEntry EntryOne(bool f32, int wg) {
   KernelEntry e;
   if (f32) {
-    if (KIND == kReproj) return e;  // fp32 storage exists for the NDT kinds only
+    if (KIND == kReproj || wg != 1) return e;  // fp32 storage exists for the NDT kinds, one tile per stage
     constexpr int K = (KIND == kReproj ? kNdt6 : KIND);
-    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<K, LOSS, float>);
-    e.smem = SmemBytes<K, float>();
-  } else {
-    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, double>);
-    e.smem = SmemBytes<KIND, double>();
+    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<K, LOSS, float, 1>);
+    e.smem = SmemBytes<K, float, 1>();
+  } else if (wg == 2) {
+    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, double, 2>);
+    e.smem = SmemBytes<KIND, double, 2>();
+  } else if (wg == 1) {
+    e.fn = reinterpret_cast<const void*>(&gn_iteration_kernel<KIND, LOSS, double, 1>);
+    e.smem = SmemBytes<KIND, double, 1>();
   }
   return e;
 }
 
 template <int KIND>
-static KernelEntry EntryKind(int loss, bool f32) {
+static KernelEntry EntryKind(int loss, bool f32, int wg) {
   switch (loss) {
-    case kLossNone: return EntryOne<KIND, kLossNone>(f32);
-    case kLossExponential: return EntryOne<KIND, kLossExponential>(f32);
-    case kLossHuber: return EntryOne<KIND, kLossHuber>(f32);
-    case kLossCauchy: return EntryOne<KIND, kLossCauchy>(f32);
+    case kLossNone: return EntryOne<KIND, kLossNone>(f32, wg);
+    case kLossExponential: return EntryOne<KIND, kLossExponential>(f32, wg);
+    case kLossHuber: return EntryOne<KIND, kLossHuber>(f32, wg);
+    case kLossCauchy: return EntryOne<KIND, kLossCauchy>(f32, wg);
   }
   return KernelEntry();
 }
 
-static KernelEntry EntryFor(int kind, int loss, bool f32) {
+static KernelEntry EntryFor(int kind, int loss, bool f32, int wg = 1) {
   switch (kind) {
-    case kNdt6: return EntryKind<kNdt6>(loss, f32);
-    case kNdt3: return EntryKind<kNdt3>(loss, f32);
-    case kReproj: return EntryKind<kReproj>(loss, f32);
+    case kNdt6: return EntryKind<kNdt6>(loss, f32, wg);
+    case kNdt3: return EntryKind<kNdt3>(loss, f32, wg);
+    case kReproj: return EntryKind<kReproj>(loss, f32, wg);
   }
   return KernelEntry();
 }
@@ -1147,13 +1179,13 @@ static int FillAttributes(cudaLaunchAttribute* attrs, bool cooperative, int clus
 }
 
 cudaError_t LaunchIteration(int kind, int loss, const IterParams& p, int grid_x, int num_problems,
-                            int cluster, cudaStream_t stream) {
-  const KernelEntry e = EntryFor(kind, loss, p.f32 != 0);
+                            int cluster, cudaStream_t stream, int warp_groups) {
+  const KernelEntry e = EntryFor(kind, loss, p.f32 != 0, warp_groups);
   if (e.fn == nullptr || cluster < 1 || cluster > kMaxCluster || grid_x % cluster != 0) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid_x, num_problems);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kThreads * warp_groups);
   cfg.dynamicSmemBytes = e.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
@@ -1231,8 +1263,8 @@ size_t IterationSmemBytes(int kind) {
 cudaError_t ConfigureKernels() {
   for (int kind = 0; kind < 3; ++kind)
     for (int loss = 0; loss < 4; ++loss)
-      for (int f32 = 0; f32 < 2; ++f32) {
-        const KernelEntry e = EntryFor(kind, loss, f32 != 0);
+      for (int variant = 0; variant < 3; ++variant) {  // fp64 one tile per stage, fp32, fp64 two tiles per stage
+        const KernelEntry e = EntryFor(kind, loss, variant == 1, variant == 2 ? 2 : 1);
         if (e.fn == nullptr) continue;
         const cudaError_t err = cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      static_cast<int>(e.smem));
