@@ -267,7 +267,7 @@ int EnqueueLoop(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_opt
     // One 512-thread CTA per SM with two tiles per ring stage instead of two 256-thread CTAs (see the
     // kernel): a single tile stream per SM, half the partials.  fp64 storage only.
     int wg = 1;
-    if (ctx->warp_groups == 2 && !pr->f32 && tiles >= 2 && (kind == kNdt3 || ctx->warp_groups_all)) {
+    if (ctx->warp_groups == 2 && !pr->f32 && tiles >= 2) {
       wg = 2;
       const int64_t stages_total = (tiles + 1) / 2;
       gx = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(stages_total, ctx->grid_small)));
@@ -730,10 +730,6 @@ int nlo_context_create(int device, nlo_context** out) {
   ctx->direct_max_clusters = env_int("NLO_DIRECT_MAX", 48, 0, 1 << 20);
   ctx->use_resident = env_int("NLO_NO_RESIDENT", 0, 0, 1) == 0;
   ctx->warp_groups = env_int("NLO_WARP_GROUPS", 2, 1, 2);
-  // Used for the planar kind only (10 accumulators): 1 - 3 % faster at every streamed size.  The 28
-  // accumulators of the 6-DoF kinds leave no register for the second warp group's indexing: ndt6 spills
-  // ~100 bytes into the tile loop and loses 14 %, PnP loses 6 %.  NLO_WARP_GROUPS_ALL=1 forces it anyway.
-  ctx->warp_groups_all = env_int("NLO_WARP_GROUPS_ALL", 0, 0, 1) != 0;
   const char* tenv = getenv("NLO_INGEST_THREADS");
   if (tenv != nullptr) ctx->ingest_threads = atoi(tenv);
   const char* denv = getenv("NLO_DEBUG_TIMES");

@@ -150,7 +150,6 @@ struct nlo_context {
   int grid_small = 0;             // CTAs of the persistent path for L2-resident problems
   int cluster_small = 8;          // NLO_CLUSTER: CTAs per thread-block cluster, problems resident in smem / L2
   int direct_max_clusters = 48;   // NLO_DIRECT_MAX: up to this many cluster partials every CTA gathers them itself
-  bool warp_groups_all = false;   // NLO_WARP_GROUPS_ALL=1: also for the 6-DoF kinds (slower: register spills)
   int warp_groups = 2;            // NLO_WARP_GROUPS: 2 = the persistent streaming loop runs one 512-thread CTA per SM
   bool use_resident = true;       // NLO_NO_RESIDENT=1: latency-bound registrations also run the streaming kernel
   int device_share = 1;           // sub-contexts of one multi-device context that sit on this device

@@ -596,6 +596,10 @@ __global__ void __launch_bounds__(kThreads * WG, WG == 1 ? 2 : 1) gn_iteration_k
     }
     st = *st_global;
   }
+  if (WG == 2 && p.mode != kModeStepOnly) {  // see the tile loop: nothing non-finite may sit in a stage
+    ST* flat = &sm.stages[0][0][0][0];
+    for (int k = tid; k < MAX_STAGES * WG * NPLANES * kTile; k += kThreads * WG) flat[k] = static_cast<ST>(0);
+  }
   __syncthreads();
 
   const Range range = p.ranges[problem];
@@ -690,27 +694,24 @@ __global__ void __launch_bounds__(kThreads * WG, WG == 1 ? 2 : 1) gn_iteration_k
             MbarWait(&sm.full[s], phase);
           }
           // this warp group's tile of the stage (the last stage of the range may not have one)
-          const int my_tile = (static_cast<int>(blockIdx.x) + m * grid_x) * WG + sub;
-          const bool have_tile = (WG == 1) || my_tile < span_tiles;
+          // (WG = 2: the last stage of the range may have no tile for the second warp group; it then
+          // computes on what the stage held before -- zeros or an earlier tile, finite either way -- and
+          // the validity test below, which covers the whole range, masks it out)
           double v[NPLANES];
-          if (have_tile) {
 #pragma unroll
-            for (int pl = 0; pl < NPLANES; ++pl) v[pl] = static_cast<double>(sm.stages[s][sub][pl][elem]);
-          }
+          for (int pl = 0; pl < NPLANES; ++pl) v[pl] = static_cast<double>(sm.stages[s][sub][pl][elem]);
           if (!resident) {
             __syncwarp();
             if (lane == 0) MbarArrive(&sm.empty[s]);
           }
-          if (have_tile) {
-            const int idx = my_tile * kTile + elem;
-            const bool valid = (idx >= valid_lo) && (idx < valid_hi);
-            if (KIND == kNdt6)
-              Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
-            else if (KIND == kNdt3)
-              Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
-            else
-              ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
-          }
+          const int idx = ((static_cast<int>(blockIdx.x) + m * grid_x) * WG + sub) * kTile + elem;
+          const bool valid = (idx >= valid_lo) && (idx < valid_hi);
+          if (KIND == kNdt6)
+            Ndt6Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+          else if (KIND == kNdt3)
+            Ndt3Point<LOSS>(v, R, t, p.loss_p0, p.loss_p1, valid, acc);
+          else
+            ReprojPoint<LOSS>(v, R, t, p.intrinsics, p.loss_p0, p.loss_p1, valid, acc);
         }
         // Warp reduction of the NACC accumulators by recursive halving: at offset 16 each lane
         // keeps half of the values and hands the other half to its partner, at offset 8 a
