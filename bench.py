@@ -428,7 +428,11 @@ def run_cuda(args):
                        "storage": "fp64, 12 scalars per correspondence: point 3 + mean 3 + S^T S (6 unique), "
                                   "S^T S formed once at ingest",
                        "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
-                             % (n_local * BYTES_PER_CORR / 1e9)},
+                             % (n_local * BYTES_PER_CORR / 1e9),
+                       "timing": "CUDA events on each rank's launch stream around the K-iteration loop, max over ranks"
+                                 + ("; a sharded Solve() opens with a device-side barrier of the ranks (one NVLink "
+                                    "exchange, in front of the start event), so the ranks' timed regions start together"
+                                    if comm == "peer" else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(n_local, args.steps if comm != "nccl" else 1),

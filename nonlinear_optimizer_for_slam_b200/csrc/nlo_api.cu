@@ -566,10 +566,15 @@ int SolveImpl(nlo_context* ctx, nlo_problem* pr, int kind, const nlo_solve_optio
   NLO_CUDA(ctx, cudaMemcpyAsync(pr->d_poses, poses, static_cast<size_t>(B) * 16 * sizeof(double),
                                 cudaMemcpyHostToDevice, ctx->stream));
   NLO_CUDA(ctx, LaunchInitStates(pr->d_states, pr->d_poses, B, kind, ctx->stream));
-  NLO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (options->max_iterations > 0) {
     if (rendezvous.active()) NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rendezvous.Sync();  // every shard is ready to launch
+    // shards on several GPUs: a device-side barrier, so that the loops and the events around them
+    // start together (the first exchange would otherwise absorb the hosts' launch skew)
+    if (CommFor(ctx, pr) == kCommPeer) NLO_CUDA(ctx, LaunchPeerRendezvous(ctx->peer, ctx->stream));
+  }
+  NLO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (options->max_iterations > 0) {
     const int rc = RunLoop(ctx, pr, kind, *options, with_trace, B, begin_abs, end_abs);
     if (rc != NLO_OK) return rc;
     rendezvous.Sync();  // every shard's loop is queued: only now may anything wait behind it

@@ -128,6 +128,7 @@ cudaError_t ConfigureKernels();
 size_t IterationSmemBytes(int kind);
 
 // Small utility kernels.
+cudaError_t LaunchPeerRendezvous(const PeerComm& pc, cudaStream_t stream);
 cudaError_t LaunchInitStates(State* states, const double* poses16, int num_problems, int kind,
                              cudaStream_t stream);
 cudaError_t LaunchFinishStates(const State* states, double* poses16, double* results4,

@@ -516,28 +516,33 @@ __device__ inline void PeerAllReduce(const PeerComm& pc, double* total, int nacc
   const unsigned int seq32 = static_cast<unsigned int>(seq);
   const int parity = static_cast<int>(seq & 1ULL);
   const int words = 2 * nacc;
-  if (tid < words) {
-    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(total[tid >> 1]));
-    const unsigned long long half = (tid & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
-    const unsigned long long word = (static_cast<unsigned long long>(seq32) << 32) | half;
-    const int slot = (parity * kMaxRanks + pc.rank) * kPeerWords + tid;
-    for (int r = 0; r < pc.nranks; ++r)
-      *reinterpret_cast<volatile unsigned long long*>(pc.slots[r] + slot) = word;
-    SpinWatch watch;
-    for (int r = 0; r < pc.nranks; ++r) {
-      const volatile unsigned long long* src =
-          reinterpret_cast<const volatile unsigned long long*>(pc.slots[pc.rank]) +
-          (parity * kMaxRanks + r) * kPeerWords + tid;
-      unsigned long long w = *src;
-      while (static_cast<unsigned int>(w >> 32) != seq32) {
-        if (watch.Expired(kPeerTimeoutNs)) {  // a peer died; fail instead of hanging
-          *pc.error = 1;
-          break;
-        }
-        w = *src;
+  // One (rank, word) item per thread, for the stores and for the polls: with the ranks walked one
+  // after the other by the same thread every rank costs a system-scope load round trip even when
+  // its words are already there (8 ranks: ~6 us of the 8-GPU step); spread over the threads the
+  // wait is one round trip after the last rank's words land.
+  const int items = pc.nranks * words;
+  const int my_slot = (parity * kMaxRanks + pc.rank) * kPeerWords;
+  for (int item = tid; item < items; item += blockDim.x) {
+    const int r = item / words, w = item - r * words;
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(total[w >> 1]));
+    const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
+    *reinterpret_cast<volatile unsigned long long*>(pc.slots[r] + my_slot + w) =
+        (static_cast<unsigned long long>(seq32) << 32) | half;
+  }
+  SpinWatch watch;
+  for (int item = tid; item < items; item += blockDim.x) {
+    const int r = item / words, w = item - r * words;
+    const volatile unsigned long long* src =
+        reinterpret_cast<const volatile unsigned long long*>(pc.slots[pc.rank]) + (parity * kMaxRanks + r) * kPeerWords + w;
+    unsigned long long v = *src;
+    while (static_cast<unsigned int>(v >> 32) != seq32) {
+      if (watch.Expired(kPeerTimeoutNs)) {  // a peer died; fail instead of hanging
+        *pc.error = 1;
+        break;
       }
-      halves[r][tid] = static_cast<unsigned int>(w);
+      v = *src;
     }
+    halves[r][w] = static_cast<unsigned int>(v);
   }
   __syncthreads();
   if (tid < nacc) {
@@ -1330,6 +1335,21 @@ __global__ void finish_states_kernel(const State* states, double* poses16, doubl
   results4[4 * i + 1] = static_cast<double>(s.status);
   results4[4 * i + 2] = s.previous_cost;
   results4[4 * i + 3] = 0.0;
+}
+
+// A barrier of the ranks on the device: one exchange of a zero.  Enqueued in front of a sharded
+// solve so that the ranks' loops (and the events around them) start together however far apart
+// their hosts reached the launch.
+__global__ void peer_rendezvous_kernel(const PeerComm pc) {
+  __shared__ double zero[1];
+  if (threadIdx.x == 0) zero[0] = 0.0;
+  __syncthreads();
+  PeerAllReduce(pc, zero, 1);
+}
+
+cudaError_t LaunchPeerRendezvous(const PeerComm& pc, cudaStream_t stream) {
+  peer_rendezvous_kernel<<<1, 32, 0, stream>>>(pc);
+  return cudaGetLastError();
 }
 
 cudaError_t LaunchInitStates(State* states, const double* poses16, int num_problems, int kind,

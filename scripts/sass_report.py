@@ -10,8 +10,10 @@ from collections import Counter
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "nonlinear_optimizer_for_slam_b200", "csrc", "nlo_kernels.o")
 KERNELS = [
-    ("streaming kernel, ndt6 / Exponential / fp64 storage  (gn_iteration_kernel<0,1,double>)",
-     "_ZN3nlo19gn_iteration_kernelILi0ELi1EdEEvNS_10IterParamsE"),
+    ("streaming kernel, ndt6 / Exponential / fp64 storage, two warp groups (default)  (gn_iteration_kernel<0,1,double,2>)",
+     "_ZN3nlo19gn_iteration_kernelILi0ELi1EdLi2EEEvNS_10IterParamsE"),
+    ("streaming kernel, ndt6 / Exponential / fp64 storage, one warp group  (gn_iteration_kernel<0,1,double,1>)",
+     "_ZN3nlo19gn_iteration_kernelILi0ELi1EdLi1EEEvNS_10IterParamsE"),
     ("resident kernel, ndt6 / Exponential  (gn_resident_kernel<0,1>)",
      "_ZN3nlo18gn_resident_kernelILi0ELi1EEEvNS_10IterParamsE"),
 ]
