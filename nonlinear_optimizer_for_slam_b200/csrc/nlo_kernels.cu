@@ -265,12 +265,17 @@ __device__ __forceinline__ unsigned long long LoadGpuU64(const unsigned long lon
 }
 
 // Fixed-order sum of `n_src` LL records of NACC doubles (record c at base + c * stride_words):
-// thread (j, l8) polls value j of records l8, l8+8, ... -- two loads in flight -- and adds them in
+// thread (j, l8) polls value j of records l8, l8+8, ... -- kGatherDepth loads in flight -- and adds them in
 // record order, then the 8 lanes are added in lane order.  total[0..NACC) is written by threads
 // 0..NACC-1 (warp 0) after an internal __syncthreads; *fail is set when a record did not show up
 // within `timeout_ns`.  Called by all threads of the CTA.  Deliberately small and NOT inlined
 // (one copy): the per-iteration code of a latency-bound registration has to stay inside the 32 KB
 // instruction cache of the SM, a miss per 128-byte line of cold code costs more than the math.
+// Loads of one polling thread in flight.  Measured per iteration, depth 2 / 4 / 6 (B200, ndt6 | ndt3):
+// 100 k points (33 records) 7.25 / 7.25 / 7.31 | 6.21 / 6.58 / 6.68 us, 200 k (74 records) 8.05 / 8.05 / 8.32
+// | 6.85 / 7.14 / 7.35, 300 k 11.68 / 11.16 / 11.05 | 9.68 / 9.29 / 8.98: more polls in flight delay the
+// very stores they wait for at the reference's sizes and only pay off above them.
+constexpr int kGatherDepth = 2;
 template <int NACC>
 __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
                                       unsigned int tag, bool sys, unsigned long long timeout_ns,
@@ -282,24 +287,32 @@ __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride
     SpinWatch watch;
     const unsigned long long* src = base + static_cast<size_t>(l8) * stride_words + 2 * j;
     const size_t step = static_cast<size_t>(8) * stride_words;
-    unsigned long long lo, hi, nlo = 0ULL, nhi = 0ULL;
-    if (l8 < n_src) LoadLL(src, lo, hi, sys);
+    // kGatherDepth records of this lane travel at once; one copy of the spin loop, the registers rotate
+    unsigned long long lo[kGatherDepth], hi[kGatherDepth];
+#pragma unroll
+    for (int u = 0; u < kGatherDepth - 1; ++u) {
+      lo[u] = hi[u] = 0ULL;
+      if (l8 + 8 * u < n_src) LoadLL(src + u * step, lo[u], hi[u], sys);
+    }
+    lo[kGatherDepth - 1] = hi[kGatherDepth - 1] = 0ULL;
 #pragma unroll 1
     for (int c = l8; c < n_src; c += 8) {
-      const bool more = c + 8 < n_src;
-      if (more) LoadLL(src + step, nlo, nhi, sys);  // the next record travels while this one is checked
-      while (static_cast<unsigned int>(lo >> 32) != tag || static_cast<unsigned int>(hi >> 32) != tag) {
+      if (c + 8 * (kGatherDepth - 1) < n_src) LoadLL(src + (kGatherDepth - 1) * step, lo[kGatherDepth - 1], hi[kGatherDepth - 1], sys);
+      while (static_cast<unsigned int>(lo[0] >> 32) != tag || static_cast<unsigned int>(hi[0] >> 32) != tag) {
         if (watch.Expired(timeout_ns)) {
           *fail = 1;
-          lo = hi = static_cast<unsigned long long>(tag) << 32;
+          lo[0] = hi[0] = static_cast<unsigned long long>(tag) << 32;
           break;
         }
-        LoadLL(src, lo, hi, sys);
+        LoadLL(src, lo[0], hi[0], sys);
       }
-      s += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
+      s += __longlong_as_double(static_cast<long long>((hi[0] << 32) | (lo[0] & 0xffffffffULL)));
       src += step;
-      lo = nlo;
-      hi = nhi;
+#pragma unroll
+      for (int u = 0; u + 1 < kGatherDepth; ++u) {
+        lo[u] = lo[u + 1];
+        hi[u] = hi[u + 1];
+      }
     }
     lanes[l8][j] = s;
   }
