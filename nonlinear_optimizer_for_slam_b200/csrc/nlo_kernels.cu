@@ -274,7 +274,9 @@ __device__ __forceinline__ unsigned long long LoadGpuU64(const unsigned long lon
 // Loads of one polling thread in flight.  Measured per iteration, depth 2 / 4 / 6 (B200, ndt6 | ndt3):
 // 100 k points (33 records) 7.25 / 7.25 / 7.31 | 6.21 / 6.58 / 6.68 us, 200 k (74 records) 8.05 / 8.05 / 8.32
 // | 6.85 / 7.14 / 7.35, 300 k 11.68 / 11.16 / 11.05 | 9.68 / 9.29 / 8.98: more polls in flight delay the
-// very stores they wait for at the reference's sizes and only pay off above them.
+// very stores they wait for at the reference's sizes and only pay off above them.  Backing off between
+// polls (__nanosleep 20 / 60 / 200 ns) was measured slower at every size (100 k ndt6: 7.96 / 8.04 / 8.30
+// against 7.22 us) and is not kept: the poll that finds the record is the one that matters.
 constexpr int kGatherDepth = 2;
 template <int NACC>
 __device__ __noinline__ void GatherLL(const unsigned long long* base, int stride_words, int n_src,
