@@ -114,6 +114,16 @@ NLO_API int nlo_set_loss(nlo_context* ctx, int kind, const double params[2]);
 NLO_API int nlo_host_alloc(void** ptr, size_t bytes);
 NLO_API int nlo_host_free(void* ptr);
 
+/* Memory-safety check of the library's own device buffers, for boxes where compute-sanitizer is not
+ * available.  With NLO_GUARD=1 in the environment when the library is first used, every device
+ * allocation sits between two 64 KB guard bands of 0xFF bytes and starts out filled with 0xFF itself
+ * (NaN as doubles): a write past either end of a buffer shows up here as corrupted guard bytes (bands
+ * are compared when a buffer is freed and, for the live ones, by this call), a read of memory nothing
+ * wrote poisons the result.  NLO_GUARD=selftest additionally overwrites one guard byte of the first
+ * allocation on purpose (the report must then say 1).  Without NLO_GUARD: *enabled = 0, zero counts. */
+NLO_API int nlo_debug_guard_report(int32_t* enabled, int64_t* allocations_checked, int64_t* allocations_live,
+                                   int64_t* corrupted_bytes);
+
 /* ---- NDT / Mahalanobis correspondences (types.h:11-26) ---- */
 /* One problem of up to `capacity` correspondences. */
 NLO_API int nlo_ndt_create(nlo_context* ctx, int64_t capacity, nlo_problem** problem);

@@ -7,4 +7,4 @@ the C++ drop-in classes under cxx/.  The Python modules here only marshal numpy 
 from . import _capi  # noqa: F401
 from .api import (Context, NdtProblem, ReprojProblem, NdtMap, Scan, Options, NloError, LOSS_NONE,  # noqa: F401
                   LOSS_EXPONENTIAL, LOSS_HUBER, LOSS_CAUCHY, identity_pose, pose_from_Rt,
-                  pose_to_Rt, host_alloc, host_free)
+                  pose_to_Rt, host_alloc, host_free, guard_report)

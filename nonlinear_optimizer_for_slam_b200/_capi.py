@@ -45,6 +45,7 @@ _SIGNATURES = {
     "nlo_set_loss": (ctypes.c_int, [_VP, ctypes.c_int, c_double_p]),
     "nlo_host_alloc": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_size_t]),
     "nlo_host_free": (ctypes.c_int, [_VP]),
+    "nlo_debug_guard_report": (ctypes.c_int, [c_int32_p, c_int64_p, c_int64_p, c_int64_p]),
     "nlo_ndt_create": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),
     "nlo_ndt_create_f32": (ctypes.c_int, [_VP, ctypes.c_int64, ctypes.POINTER(_VP)]),
     "nlo_ndt_create_batched": (ctypes.c_int, [_VP, ctypes.c_int32, c_int64_p, ctypes.POINTER(_VP)]),

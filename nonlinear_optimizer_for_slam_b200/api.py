@@ -482,3 +482,14 @@ def host_alloc(nbytes):
 
 def host_free(p):
     _capi.load().nlo_host_free(p)
+
+
+def guard_report():
+    """State of the guard-band check of the library's device buffers (nlo_debug_guard_report;
+    active when NLO_GUARD=1 was in the environment before the library's first allocation)."""
+    en = ctypes.c_int32(0)
+    checked, live, bad = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    _capi.load().nlo_debug_guard_report(ctypes.byref(en), ctypes.byref(checked), ctypes.byref(live),
+                                        ctypes.byref(bad))
+    return {"enabled": bool(en.value), "allocations_checked": checked.value,
+            "allocations_live": live.value, "corrupted_bytes": bad.value}

@@ -49,7 +49,7 @@ def build_cuda(force=False, verbose=False):
             print(out.decode())
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-ldl", "-lpthread"]
+    link = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH] + objs + ["-lcudart", "-ldl", "-lpthread"]
     subprocess.run(link, check=True)
     return LIB_PATH
 

@@ -362,15 +362,122 @@ int Fail(nlo_context* ctx, int code, const std::string& msg) {
   return code;
 }
 
+// ---- device allocations, optionally guarded (NLO_GUARD=1; see nlo_host.h) ----
+namespace {
+constexpr size_t kGuardBytes = 64 * 1024;  // more than two tiles of any kind (24 KB), a whole LL partial row
+struct GuardedBlock {
+  size_t bytes;  // payload
+  int device;
+};
+struct GuardState {
+  std::mutex mu;
+  std::map<void*, GuardedBlock> live;  // payload pointer -> block
+  int64_t checked = 0;                 // allocations whose bands were compared when they were freed
+  int64_t corrupted_bytes = 0;         // guard bytes found != 0xFF, freed allocations
+  int64_t peak_live = 0;
+  bool selftest_pending = false;       // NLO_GUARD=selftest: one byte of the first tail band is overwritten on purpose
+};
+GuardState& Guards() {
+  static GuardState g;
+  return g;
+}
+int GuardMode() {  // 0 off, 1 on, 2 on + the deliberate overrun that proves the check sees one
+  static const int mode = [] {
+    const char* v = getenv("NLO_GUARD");
+    if (v == nullptr || v[0] == '\0' || v[0] == '0') return 0;
+    if (strcmp(v, "selftest") == 0) {
+      Guards().selftest_pending = true;
+      return 2;
+    }
+    return 1;
+  }();
+  return mode;
+}
+// bytes != 0xFF in the two bands around `payload` (on the device that owns it)
+int64_t CountGuardDamage(void* payload, const GuardedBlock& b) {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(b.device);
+  cudaDeviceSynchronize();  // the library's streams are non-blocking: a plain cudaMemcpy does not wait for them
+  std::vector<unsigned char> host(2 * kGuardBytes);
+  unsigned char* base = static_cast<unsigned char*>(payload) - kGuardBytes;
+  const size_t tail_offset = kGuardBytes + ((b.bytes + 255) / 256) * 256;
+  int64_t bad = 0;
+  if (cudaMemcpy(host.data(), base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(host.data() + kGuardBytes, base + tail_offset, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    bad = -1;
+  } else {
+    for (unsigned char c : host) bad += (c != 0xFF) ? 1 : 0;
+  }
+  cudaSetDevice(prev);
+  return bad;
+}
+}  // namespace
+
+cudaError_t DevMallocBytes(void** p, size_t bytes) {
+  if (GuardMode() == 0) return cudaMalloc(p, bytes);
+  *p = nullptr;
+  // [front band][payload, rounded up to 256 B so that the tail band (and TMA sources) stay aligned][tail band]
+  const size_t padded = ((bytes + 255) / 256) * 256;
+  unsigned char* base = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), padded + 2 * kGuardBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, 0xFF, padded + 2 * kGuardBytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(base);
+    return e;
+  }
+  GuardedBlock b{bytes, 0};
+  cudaGetDevice(&b.device);
+  GuardState& g = Guards();
+  {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (g.selftest_pending) {
+      g.selftest_pending = false;
+      cudaMemset(base + kGuardBytes + padded + 5, 0x00, 1);  // the overrun the self-test expects to be reported
+      cudaDeviceSynchronize();
+    }
+    g.live[base + kGuardBytes] = b;
+    g.peak_live = std::max<int64_t>(g.peak_live, static_cast<int64_t>(g.live.size()));
+  }
+  *p = base + kGuardBytes;
+  return cudaSuccess;
+}
+
+cudaError_t DevFree(void* p) {
+  if (p == nullptr || GuardMode() == 0) return cudaFree(p);
+  GuardState& g = Guards();
+  GuardedBlock b{0, 0};
+  {
+    std::lock_guard<std::mutex> lock(g.mu);
+    auto it = g.live.find(p);
+    if (it == g.live.end()) return cudaFree(p);
+    b = it->second;
+    g.live.erase(it);
+  }
+  const int64_t bad = CountGuardDamage(p, b);
+  {
+    std::lock_guard<std::mutex> lock(g.mu);
+    g.checked += 1;
+    g.corrupted_bytes += (bad < 0) ? 1 : bad;
+  }
+  if (bad != 0)
+    fprintf(stderr, "[nlo guard] %lld damaged guard byte(s) around a %zu-byte device allocation\n",
+            static_cast<long long>(bad), b.bytes);
+  return cudaFree(static_cast<unsigned char*>(p) - kGuardBytes);
+}
+
 int EnsureStaging(nlo_context* ctx, size_t bytes) {
   if (bytes <= ctx->staging_bytes) return NLO_OK;
   if (ctx->staging != nullptr) {
     NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    NLO_CUDA(ctx, cudaFree(ctx->staging));
+    NLO_CUDA(ctx, DevFree(ctx->staging));
     ctx->staging = nullptr;
     ctx->staging_bytes = 0;
   }
-  NLO_CUDA(ctx, cudaMalloc(&ctx->staging, bytes));
+  NLO_CUDA(ctx, DevMalloc(&ctx->staging, bytes));
   ctx->staging_bytes = bytes;
   return NLO_OK;
 }
@@ -424,31 +531,31 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
       return fail_free((_e == cudaErrorMemoryAllocation) ? NLO_ENOMEM : NLO_ECUDA,     \
                        std::string(#expr) + ": " + cudaGetErrorString(_e));            \
   } while (0)
-  NLO_CUDA_P(cudaMalloc(&pr->plane_block, plane_bytes * pr->num_planes));
+  NLO_CUDA_P(DevMalloc(&pr->plane_block, plane_bytes * pr->num_planes));
   NLO_CUDA_P(cudaMemsetAsync(pr->plane_block, 0, plane_bytes * pr->num_planes, ctx->stream));
   // tile-interleaved layout: plane k of tile 0 starts at k * 256 (nlo_internal.h TiledOffset)
   for (int k = 0; k < pr->num_planes; ++k)
     pr->planes[k] = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(pr->plane_block) +
                                               static_cast<size_t>(k) * kTile * elem);
   const int slots = num_problems + 1;
-  NLO_CUDA_P(cudaMalloc(&pr->d_ranges, slots * sizeof(Range)));
-  NLO_CUDA_P(cudaMalloc(&pr->d_states, slots * sizeof(State)));
+  NLO_CUDA_P(DevMalloc(&pr->d_ranges, slots * sizeof(Range)));
+  NLO_CUDA_P(DevMalloc(&pr->d_states, slots * sizeof(State)));
   // per-CTA partials [2 parities][grid rows x CTAs per row][28]: a single problem uses up to
   // grid_single CTAs, a small batch num_problems x (grid_single / num_problems) <= grid_single
-  NLO_CUDA_P(cudaMalloc(&pr->d_partials,
+  NLO_CUDA_P(DevMalloc(&pr->d_partials,
                         2 * static_cast<size_t>(std::max(ctx->grid_single, 1)) * kAcc6 * sizeof(double)));
   // cluster partials of the persistent path as LL words: [2 parities][<= grid_single clusters][28][2]
   pr->ll_partials_bytes = 2 * static_cast<size_t>(std::max(ctx->grid_single, 1) + kMaxCluster) * kAcc6 * 2 * sizeof(unsigned long long);
-  NLO_CUDA_P(cudaMalloc(&pr->d_ll_partials, pr->ll_partials_bytes));
+  NLO_CUDA_P(DevMalloc(&pr->d_ll_partials, pr->ll_partials_bytes));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_ll_partials, 0, pr->ll_partials_bytes, ctx->stream));
-  NLO_CUDA_P(cudaMalloc(&pr->d_sync, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long)));
+  NLO_CUDA_P(DevMalloc(&pr->d_sync, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_sync, 0, static_cast<size_t>(slots) * kSyncStride * sizeof(unsigned long long), ctx->stream));
-  NLO_CUDA_P(cudaMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
+  NLO_CUDA_P(DevMalloc(&pr->d_tickets, slots * sizeof(unsigned int)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_tickets, 0, slots * sizeof(unsigned int), ctx->stream));
-  NLO_CUDA_P(cudaMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
+  NLO_CUDA_P(DevMalloc(&pr->d_sums, slots * 32 * sizeof(double)));
   NLO_CUDA_P(cudaMemsetAsync(pr->d_sums, 0, slots * 32 * sizeof(double), ctx->stream));
-  NLO_CUDA_P(cudaMalloc(&pr->d_poses, slots * 16 * sizeof(double)));
-  NLO_CUDA_P(cudaMalloc(&pr->d_results, slots * 4 * sizeof(double)));
+  NLO_CUDA_P(DevMalloc(&pr->d_poses, slots * 16 * sizeof(double)));
+  NLO_CUDA_P(DevMalloc(&pr->d_results, slots * 4 * sizeof(double)));
   NLO_CUDA_P(cudaMemcpyAsync(pr->d_ranges, pr->h_ranges.data(), num_problems * sizeof(Range),
                              cudaMemcpyHostToDevice, ctx->stream));
   NLO_CUDA_P(cudaStreamSynchronize(ctx->stream));
@@ -464,10 +571,10 @@ int CreateProblem(nlo_context* ctx, int family, int num_problems, const int64_t*
 int EnsureTrace(nlo_context* ctx, nlo_problem* pr, size_t need_doubles) {
   if (need_doubles <= pr->trace_doubles) return NLO_OK;
   NLO_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (pr->d_trace) NLO_CUDA(ctx, cudaFree(pr->d_trace));
+  if (pr->d_trace) NLO_CUDA(ctx, DevFree(pr->d_trace));
   pr->d_trace = nullptr;
   pr->trace_doubles = 0;
-  NLO_CUDA(ctx, cudaMalloc(&pr->d_trace, need_doubles * sizeof(double)));
+  NLO_CUDA(ctx, DevMalloc(&pr->d_trace, need_doubles * sizeof(double)));
   pr->trace_doubles = need_doubles;
   DropGraphs(pr);
   return NLO_OK;
@@ -743,7 +850,7 @@ int nlo_context_create(int device, nlo_context** out) {
     // $NLO_DEBUG_FILE (raw u64 [kDebugCtas][kDebugIterations][8], slot 7 of iteration 0 = SM id)
     ctx->debug_all_ctas = denv[0] == '2';
     const size_t bytes = static_cast<size_t>(kDebugCtas) * kDebugIterations * kDebugSlots * sizeof(unsigned long long);
-    cudaMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), bytes);
+    DevMalloc(reinterpret_cast<void**>(&ctx->d_debug_times), bytes);
     cudaMemset(ctx->d_debug_times, 0, bytes);
   }
   const char* genv = getenv("NLO_GRID");
@@ -785,13 +892,50 @@ int nlo_context_destroy(nlo_context* ctx) {
   ctx->reg_workspace = nullptr;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   FreeIngestRing(ctx);
-  if (ctx->staging) cudaFree(ctx->staging);
-  if (ctx->d_debug_times) cudaFree(ctx->d_debug_times);
+  if (ctx->staging) DevFree(ctx->staging);
+  if (ctx->d_debug_times) DevFree(ctx->d_debug_times);
   if (ctx->host_small) cudaFreeHost(ctx->host_small);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return NLO_OK;
+}
+
+int nlo_debug_guard_report(int32_t* enabled, int64_t* allocations_checked, int64_t* allocations_live,
+                           int64_t* corrupted_bytes) {
+  const int mode = GuardMode();
+  if (enabled) *enabled = mode != 0 ? 1 : 0;
+  int64_t checked = 0, live = 0, bad = 0;
+  if (mode != 0) {
+    GuardState& g = Guards();
+    std::map<void*, GuardedBlock> snapshot;
+    {
+      std::lock_guard<std::mutex> lock(g.mu);
+      snapshot = g.live;
+      checked = g.checked;
+      bad = g.corrupted_bytes;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess) {
+      int prev = 0;
+      cudaGetDevice(&prev);
+      for (int d = 0; d < count; ++d) {
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+      }
+      cudaSetDevice(prev);
+    }
+    for (const auto& kv : snapshot) {
+      const int64_t b = CountGuardDamage(kv.first, kv.second);
+      bad += (b < 0) ? 1 : b;
+      checked += 1;
+    }
+    live = static_cast<int64_t>(snapshot.size());
+  }
+  if (allocations_checked) *allocations_checked = checked;
+  if (allocations_live) *allocations_live = live;
+  if (corrupted_bytes) *corrupted_bytes = bad;
   return NLO_OK;
 }
 
@@ -937,17 +1081,17 @@ int nlo_problem_destroy(nlo_context* ctx, nlo_problem* pr) {
     cudaStreamSynchronize(ctx->stream);
   }
   DropGraphs(pr);
-  cudaFree(pr->plane_block);
-  cudaFree(pr->d_ranges);
-  cudaFree(pr->d_states);
-  cudaFree(pr->d_partials);
-  cudaFree(pr->d_tickets);
-  cudaFree(pr->d_sync);
-  cudaFree(pr->d_ll_partials);
-  cudaFree(pr->d_sums);
-  cudaFree(pr->d_poses);
-  cudaFree(pr->d_results);
-  cudaFree(pr->d_trace);
+  DevFree(pr->plane_block);
+  DevFree(pr->d_ranges);
+  DevFree(pr->d_states);
+  DevFree(pr->d_partials);
+  DevFree(pr->d_tickets);
+  DevFree(pr->d_sync);
+  DevFree(pr->d_ll_partials);
+  DevFree(pr->d_sums);
+  DevFree(pr->d_poses);
+  DevFree(pr->d_results);
+  DevFree(pr->d_trace);
   delete pr;
   return NLO_OK;
 }
@@ -1150,9 +1294,9 @@ int nlo_comm_peer_export(nlo_context* ctx, uint8_t handle[64]) {
   if (ctx->peer_buf == nullptr) {
     NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->peer_buf), kPeerBufBytes));
     NLO_CUDA(ctx, cudaMemset(ctx->peer_buf, 0, kPeerBufBytes));
-    NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_peer_seq), sizeof(unsigned long long)));
+    NLO_CUDA(ctx, DevMalloc(reinterpret_cast<void**>(&ctx->d_peer_seq), sizeof(unsigned long long)));
     NLO_CUDA(ctx, cudaMemset(ctx->d_peer_seq, 0, sizeof(unsigned long long)));
-    NLO_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_peer_error), sizeof(int)));
+    NLO_CUDA(ctx, DevMalloc(reinterpret_cast<void**>(&ctx->d_peer_error), sizeof(int)));
     NLO_CUDA(ctx, cudaMemset(ctx->d_peer_error, 0, sizeof(int)));
     NLO_CUDA(ctx, cudaDeviceSynchronize());
   }
@@ -1240,8 +1384,8 @@ int nlo_comm_destroy(nlo_context* ctx) {
     }
   }
   if (ctx->peer_buf) { cudaFree(ctx->peer_buf); ctx->peer_buf = nullptr; }
-  if (ctx->d_peer_seq) { cudaFree(ctx->d_peer_seq); ctx->d_peer_seq = nullptr; }
-  if (ctx->d_peer_error) { cudaFree(ctx->d_peer_error); ctx->d_peer_error = nullptr; }
+  if (ctx->d_peer_seq) { DevFree(ctx->d_peer_seq); ctx->d_peer_seq = nullptr; }
+  if (ctx->d_peer_error) { DevFree(ctx->d_peer_error); ctx->d_peer_error = nullptr; }
   ctx->comm_kind = kCommNone;
   ctx->comm_in_process = false;
   ctx->comm_suspended = false;

@@ -256,6 +256,20 @@ int Fail(nlo_context* ctx, int code, const std::string& msg);
     }                                                                                    \
   } while (0)
 
+// Device allocations of the library (nlo_api.cu).  Plain cudaMalloc / cudaFree unless NLO_GUARD=1 is in
+// the environment -- the memory-safety check that stands in for compute-sanitizer where that tool is
+// not available: every allocation then sits between two 64 KB guard bands filled with 0xFF, and its
+// payload is pre-filled with 0xFF too (as doubles NaN, as LL tags a value no iteration uses, as
+// counters / indices absurd), so a write past either end of a buffer is found when the bands are
+// compared (at cudaFree time and by nlo_debug_guard_report), and a read of memory nothing wrote, or
+// just outside a buffer, poisons the result the parity tests look at.
+cudaError_t DevMallocBytes(void** p, size_t bytes);
+template <typename T>
+cudaError_t DevMalloc(T** p, size_t bytes) {
+  return DevMallocBytes(reinterpret_cast<void**>(p), bytes);
+}
+cudaError_t DevFree(void* p);
+
 int EnsureStaging(nlo_context* ctx, size_t bytes);
 void DropGraphs(nlo_problem* pr);
 void PoseToRt(const double pose[16], double R[9], double t[3]);

@@ -117,7 +117,7 @@ int EnsureRing(nlo_context* ctx, size_t chunk_bytes) {
   for (int k = 0; k < IngestRing::kSlots && e == cudaSuccess; ++k) {
     e = cudaHostAlloc(reinterpret_cast<void**>(&r.host[k]), chunk_bytes, cudaHostAllocDefault);
     if (e == cudaSuccess) memset(r.host[k], 0, chunk_bytes);  // first touch under the preferred-node policy
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&r.device[k]), chunk_bytes);
+    if (e == cudaSuccess) e = DevMalloc(reinterpret_cast<void**>(&r.device[k]), chunk_bytes);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.done[k], cudaEventDisableTiming);
   }
   DefaultMemPolicy();
@@ -299,7 +299,7 @@ void FreeIngestRing(nlo_context* ctx) {
   IngestRing& r = ctx->ring;
   for (int k = 0; k < IngestRing::kSlots; ++k) {
     if (r.host[k]) cudaFreeHost(r.host[k]);
-    if (r.device[k]) cudaFree(r.device[k]);
+    if (r.device[k]) DevFree(r.device[k]);
     if (r.done[k]) cudaEventDestroy(r.done[k]);
     r.host[k] = nullptr;
     r.device[k] = nullptr;

@@ -75,10 +75,10 @@ int AllocMap(nlo_context* ctx, const double origin[3], const int32_t dims[3], do
   m->voxel = voxel;
   m->cells = cells;
   m->hash_mask = hash_slots ? hash_slots - 1 : 0;
-  if (cudaMalloc(&m->d_mean, cells * 3 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&m->d_sqrt_info, cells * 9 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&m->d_valid, cells) != cudaSuccess ||
-      (hash_slots && cudaMalloc(&m->d_keys, cells * sizeof(unsigned long long)) != cudaSuccess)) {
+  if (DevMalloc(&m->d_mean, cells * 3 * sizeof(double)) != cudaSuccess ||
+      DevMalloc(&m->d_sqrt_info, cells * 9 * sizeof(double)) != cudaSuccess ||
+      DevMalloc(&m->d_valid, cells) != cudaSuccess ||
+      (hash_slots && DevMalloc(&m->d_keys, cells * sizeof(unsigned long long)) != cudaSuccess)) {
     nlo_ndt_map_destroy(ctx, m);
     return Fail(ctx, NLO_ENOMEM, "cudaMalloc(map) failed");
   }
@@ -208,7 +208,7 @@ int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel
     // pass 1: distinct occupied voxels, through a scratch key table of >= 2 n slots
     const int64_t scratch_slots = NextPow2(std::max<int64_t>(2 * n, 1024));
     unsigned long long* d_scratch = nullptr;
-    if (cudaMalloc(&d_scratch, (scratch_slots + 1) * sizeof(unsigned long long)) != cudaSuccess) {
+    if (DevMalloc(&d_scratch, (scratch_slots + 1) * sizeof(unsigned long long)) != cudaSuccess) {
       cudaGetLastError();
       return Fail(ctx, NLO_ENOMEM, "cudaMalloc(voxel hash scratch) failed");
     }
@@ -220,7 +220,7 @@ int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel
     unsigned long long distinct = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->host_small, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_scratch);
+    DevFree(d_scratch);
     if (e != cudaSuccess) return Fail(ctx, NLO_ECUDA, std::string("map build (voxel count): ") + cudaGetErrorString(e));
     memcpy(&distinct, ctx->host_small, sizeof(distinct));
     if (static_cast<int64_t>(distinct) > kMaxMapCells) return Fail(ctx, NLO_EINVAL, "more than 2^28 occupied voxels");
@@ -232,9 +232,9 @@ int BuildMap(nlo_context* ctx, int64_t n, const double* points_xyz, double voxel
   if (rc != NLO_OK) return rc;
   int* d_count = nullptr;
   double* d_sums = nullptr;
-  auto cleanup = [&]() { cudaFree(d_count); cudaFree(d_sums); };
-  cudaError_t e = cudaMalloc(&d_count, m->cells * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&d_sums, m->cells * 9 * sizeof(double));
+  auto cleanup = [&]() { DevFree(d_count); DevFree(d_sums); };
+  cudaError_t e = DevMalloc(&d_count, m->cells * sizeof(int));
+  if (e == cudaSuccess) e = DevMalloc(&d_sums, m->cells * 9 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, m->cells * sizeof(int), ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, m->cells * 9 * sizeof(double), ctx->stream);
   if (e == cudaSuccess && hashed) e = cudaMemsetAsync(m->d_keys, 0xff, m->cells * sizeof(unsigned long long), ctx->stream);
@@ -334,10 +334,10 @@ int nlo_ndt_map_destroy(nlo_context* ctx, nlo_ndt_map* map) {
   NLO_ON_FIRST_DEVICE(ctx, nlo_ndt_map_destroy(sub, map));
   if (map == nullptr) return NLO_OK;
   if (ctx != nullptr) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  cudaFree(map->d_mean);
-  cudaFree(map->d_sqrt_info);
-  cudaFree(map->d_valid);
-  cudaFree(map->d_keys);
+  DevFree(map->d_mean);
+  DevFree(map->d_sqrt_info);
+  DevFree(map->d_valid);
+  DevFree(map->d_keys);
   delete map;
   return NLO_OK;
 }
@@ -350,7 +350,7 @@ int nlo_scan_create(nlo_context* ctx, int64_t n, const double* points_xyz, nlo_s
   sc->n = n;
   const int64_t cap = std::max<int64_t>(n, 1);
   // one allocation: three planes + the matched-correspondence counter behind them
-  if (cudaMalloc(&sc->block, (cap * 3 + 8) * sizeof(double)) != cudaSuccess) {
+  if (DevMalloc(&sc->block, (cap * 3 + 8) * sizeof(double)) != cudaSuccess) {
     nlo_scan_destroy(ctx, sc);
     return Fail(ctx, NLO_ENOMEM, "cudaMalloc(scan) failed");
   }
@@ -376,7 +376,7 @@ int nlo_scan_destroy(nlo_context* ctx, nlo_scan* scan) {
   NLO_ON_FIRST_DEVICE(ctx, nlo_scan_destroy(sub, scan));
   if (scan == nullptr) return NLO_OK;
   if (ctx != nullptr) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  cudaFree(scan->block);
+  DevFree(scan->block);
   delete scan;
   return NLO_OK;
 }

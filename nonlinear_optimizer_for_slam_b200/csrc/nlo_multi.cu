@@ -209,9 +209,9 @@ int CreateContext(const int* devices, int n, nlo_context** out) {
       cudaError_t e = cudaSetDevice(sub->device);
       if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sub->peer_buf), kPeerBufBytes);
       if (e == cudaSuccess) e = cudaMemset(sub->peer_buf, 0, kPeerBufBytes);
-      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sub->d_peer_seq), sizeof(unsigned long long));
+      if (e == cudaSuccess) e = DevMalloc(reinterpret_cast<void**>(&sub->d_peer_seq), sizeof(unsigned long long));
       if (e == cudaSuccess) e = cudaMemset(sub->d_peer_seq, 0, sizeof(unsigned long long));
-      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sub->d_peer_error), sizeof(int));
+      if (e == cudaSuccess) e = DevMalloc(reinterpret_cast<void**>(&sub->d_peer_error), sizeof(int));
       if (e == cudaSuccess) e = cudaMemset(sub->d_peer_error, 0, sizeof(int));
       if (e == cudaSuccess) e = cudaDeviceSynchronize();
       if (e != cudaSuccess) return fail(NLO_ECUDA, std::string("exchange buffer: ") + cudaGetErrorString(e));

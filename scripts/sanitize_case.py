@@ -1,4 +1,8 @@
-"""Small end-to-end case for compute-sanitizer (memcheck / racecheck): every launch shape once."""
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck) or, where that tool is closed,
+for the library's own guard bands (NLO_GUARD=1, include/nlo_cuda.h nlo_debug_guard_report): every
+launch shape once, the map builder, the matcher and the outer registration loop; prints the guard
+report as the last line (GUARD {json})."""
+import json
 import os
 import sys
 
@@ -35,5 +39,27 @@ X, px, K = syn.pnp_fixture()
 pr = nlo.ReprojProblem(ctx, capacity=len(X)); pr.upload(X, px, K)
 print("pnp", pr.solve(pose0)["iterations"])
 pr.close()
+# device map (dense and hashed), matcher, outer registration loop (6-DoF and planar)
+rng = np.random.default_rng(11)
+cloud = syn.room_surface_samples(60000, rng, 0.005)
+local = syn.room_surface_samples(5000, rng, 0.005)
+for hashed in (False, True):
+    m = nlo.NdtMap(ctx, points=cloud, voxel=1.0, hashed=hashed)
+    sc = nlo.Scan(ctx, local)
+    for three in (False, True):
+        print("register hashed=%s planar=%s" % (hashed, three),
+              sc.register(m, pose0, nlo.Options(max_iterations=5), max_outer=3, three_dof=three)["outer_iterations"])
+    sc.close(); m.close()
+# sharded over a device list (the same device twice: peer exchange, host rendezvous)
+mctx = nlo.Context(devices=[0, 0])
+pr = nlo.NdtProblem(mctx, capacity=120001)
+pr.generate(120001, 7, 0, 0.01, syn.to_pose16(syn.CFG1_TRUE), pose0, grid)
+mctx.set_loss(nlo.LOSS_EXPONENTIAL, [1.0, 1.0])
+print("sharded ndt6", pr.solve6(pose0, nlo.Options(max_iterations=6))["iterations"])
+mctx.set_loss(nlo.LOSS_HUBER, [1.0])
+print("sharded ndt3", pr.solve3(pose0, nlo.Options(max_iterations=6))["iterations"])
+pr.close()
+mctx.close()
 ctx.close()
 print("SANITIZE_CASE_DONE")
+print("GUARD " + json.dumps(nlo.guard_report()))

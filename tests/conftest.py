@@ -31,3 +31,22 @@ def ctx(nlo):
     c = nlo.Context(0)
     yield c
     c.close()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """NLO_GUARD=1 python -m pytest tests -m gpu: the whole GPU suite runs with guard bands around every
+    device buffer of the library (include/nlo_cuda.h, nlo_debug_guard_report); damaged bands fail the run."""
+    if os.environ.get("NLO_GUARD", "0") in ("", "0"):
+        return
+    pkg = sys.modules.get("nonlinear_optimizer_for_slam_b200")
+    if pkg is None:
+        return
+    rep = pkg.guard_report()
+    print("\n[nlo guard] %s" % rep)
+    out = os.environ.get("NLO_GUARD_REPORT")
+    if out:
+        import json
+        with open(out, "w") as f:
+            json.dump(rep, f)
+    if rep["enabled"] and rep["corrupted_bytes"] != 0 and os.environ["NLO_GUARD"] != "selftest":
+        session.exitstatus = 1
