@@ -892,6 +892,7 @@ int nlo_context_destroy(nlo_context* ctx) {
   ctx->reg_workspace = nullptr;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   FreeIngestRing(ctx);
+  FreeIngestPool(ctx);
   if (ctx->staging) DevFree(ctx->staging);
   if (ctx->d_debug_times) DevFree(ctx->d_debug_times);
   if (ctx->host_small) cudaFreeHost(ctx->host_small);

@@ -174,6 +174,8 @@ struct nlo_context {
   // ingest pipeline
   nlo::IngestRing ring;
   int ingest_threads = 0;  // host threads one upload may use (NLO_INGEST_THREADS; 0 = decide per call)
+  std::vector<nlo::Worker*> ingest_pool;  // persistent gather threads (created on the first threaded upload)
+  int numa_node = -2;                     // NUMA node of the device's PCIe root (-1 unknown, -2 not looked up yet)
   double last_ingest_ms = 0.0, last_ingest_gather_ms = 0.0;  // wall time of the last upload / its host gather
   // multi-device context (nlo_context_create_multi): this object is then only a dispatcher
   std::vector<nlo_context*> subs;
@@ -302,6 +304,7 @@ int GenerateNdt(nlo_context* ctx, nlo_problem* pr, uint64_t seed, int64_t global
 int DownloadNdt(nlo_context* ctx, const nlo_problem* pr, int32_t problem_index, int64_t begin, int64_t end,
                 double* point, double* mean, double* information);
 void FreeIngestRing(nlo_context* ctx);
+void FreeIngestPool(nlo_context* ctx);
 
 // nlo_multi.cu
 namespace multi {

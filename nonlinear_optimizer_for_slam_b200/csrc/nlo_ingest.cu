@@ -111,8 +111,8 @@ int EnsureRing(nlo_context* ctx, size_t chunk_bytes) {
   if (chunk_bytes <= r.chunk_bytes) return NLO_OK;
   NLO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   FreeIngestRing(ctx);
-  const int node = DeviceNumaNode(ctx->device);
-  PreferNode(node);
+  if (ctx->numa_node == -2) ctx->numa_node = DeviceNumaNode(ctx->device);
+  PreferNode(ctx->numa_node);
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < IngestRing::kSlots && e == cudaSuccess; ++k) {
     e = cudaHostAlloc(reinterpret_cast<void**>(&r.host[k]), chunk_bytes, cudaHostAllocDefault);
@@ -138,6 +138,28 @@ bool IsPinned(const void* p) {
     return false;
   }
   return a.type == cudaMemoryTypeHost;
+}
+
+// Persistent gather threads of a context, bound (once) to the CPUs of the device's NUMA node; returns
+// how many of the `want` helpers exist.
+int EnsureIngestPool(nlo_context* ctx, int want) {
+  if (static_cast<int>(ctx->ingest_pool.size()) >= want) return want;
+  if (ctx->numa_node == -2) ctx->numa_node = DeviceNumaNode(ctx->device);
+  const std::vector<int> cpus = NodeCpus(ctx->numa_node);
+  while (static_cast<int>(ctx->ingest_pool.size()) < want) {
+    Worker* w = new Worker();
+    if (!cpus.empty()) {
+      w->Post([cpus]() {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int c : cpus) CPU_SET(c, &set);
+        sched_setaffinity(0, sizeof(set), &set);
+      });
+      w->Wait();
+    }
+    ctx->ingest_pool.push_back(w);
+  }
+  return want;
 }
 
 int ThreadsFor(const nlo_context* ctx, int64_t n) {
@@ -173,42 +195,50 @@ int PipelinedIngest(nlo_context* ctx, int64_t n, size_t rec_bytes, bool host_fil
   for (int k = 0; k < IngestRing::kSlots; ++k) ring.used[k] = false;
 
   const int T = host_fill ? ThreadsFor(ctx, n) : 1;
-  // filled[c] = parts of chunk c written; free_upto = chunks whose slot may be overwritten
-  std::vector<std::atomic<int>> filled(static_cast<size_t>(num_chunks));
+  // Host gather: every chunk is cut into blocks that the threads CLAIM (an atomic cursor per chunk), so
+  // a helper that wakes late simply takes fewer blocks instead of holding up the chunk.  The helpers
+  // are persistent workers of the context (EnsureIngestPool): an upload of the reference's size
+  // (100 k records, 0.3 ms of PCIe time) cannot afford to create a dozen threads.
+  // next[c] = next unclaimed block of chunk c, filled[c] = blocks written; free_upto = chunks whose
+  // slot may be overwritten
+  int per_thread = 4;
+  if (const char* v = getenv("NLO_INGEST_BLOCKS")) per_thread = std::max(1, std::min(16, atoi(v)));
+  const int blocks = (T > 1) ? static_cast<int>(std::max<int64_t>(T, std::min<int64_t>(static_cast<int64_t>(per_thread) * T, chunk / 1024))) : 1;
+  std::vector<std::atomic<int>> next(static_cast<size_t>(num_chunks)), filled(static_cast<size_t>(num_chunks));
+  for (auto& f : next) f.store(0, std::memory_order_relaxed);
   for (auto& f : filled) f.store(0, std::memory_order_relaxed);
   std::atomic<int64_t> free_upto{0};
   std::atomic<bool> abort{false};
-  auto fill_part = [&](int64_t c, int part) {
+  auto fill_blocks = [&](int64_t c) {
     const int64_t first = c * chunk;
     const int64_t count = std::min(chunk, n - first);
-    fill(ring.host[c % IngestRing::kSlots], first, count, part, T);
-    filled[static_cast<size_t>(c)].fetch_add(1, std::memory_order_release);
+    unsigned char* host = ring.host[c % IngestRing::kSlots];
+    for (;;) {
+      const int b = next[static_cast<size_t>(c)].fetch_add(1, std::memory_order_relaxed);
+      if (b >= blocks) return;
+      fill(host, first, count, b, blocks);
+      filled[static_cast<size_t>(c)].fetch_add(1, std::memory_order_release);
+    }
   };
-  std::vector<std::thread> helpers;
+  int helpers = 0;
   if (T > 1) {
-    const std::vector<int> cpus = NodeCpus(DeviceNumaNode(ctx->device));
-    for (int t = 1; t < T; ++t) {
-      helpers.emplace_back([&, t]() {
-        if (!cpus.empty()) {
-          cpu_set_t set;
-          CPU_ZERO(&set);
-          for (int c : cpus) CPU_SET(c, &set);
-          sched_setaffinity(0, sizeof(set), &set);
-        }
+    helpers = EnsureIngestPool(ctx, T - 1);
+    for (int t = 0; t < helpers; ++t) {
+      ctx->ingest_pool[static_cast<size_t>(t)]->Post([&]() {
         for (int64_t c = 0; c < num_chunks; ++c) {
           while (free_upto.load(std::memory_order_acquire) <= c) {
             if (abort.load(std::memory_order_relaxed)) return;
             std::this_thread::yield();
           }
-          fill_part(c, t);
+          fill_blocks(c);
         }
       });
     }
   }
   auto join_all = [&]() {
     abort.store(true);
-    for (auto& h : helpers) h.join();
-    helpers.clear();
+    for (int t = 0; t < helpers; ++t) ctx->ingest_pool[static_cast<size_t>(t)]->Wait();
+    helpers = 0;
   };
   double gather_ms = 0.0;
   cudaError_t e = cudaSuccess;
@@ -221,8 +251,8 @@ int PipelinedIngest(nlo_context* ctx, int64_t n, size_t rec_bytes, bool host_fil
       if (e != cudaSuccess) break;
       const auto t0 = Clock::now();
       free_upto.store(c + 1, std::memory_order_release);
-      fill_part(c, 0);
-      while (filled[static_cast<size_t>(c)].load(std::memory_order_acquire) < T) std::this_thread::yield();
+      fill_blocks(c);
+      while (filled[static_cast<size_t>(c)].load(std::memory_order_acquire) < blocks) std::this_thread::yield();
       gather_ms += MsSince(t0);
     }
     e = copy(ring.device[slot], ring.host[slot], first, count);
@@ -294,6 +324,11 @@ int CheckCount(nlo_context* ctx, const nlo_problem* pr, int64_t n) {
 }
 
 }  // namespace
+
+void FreeIngestPool(nlo_context* ctx) {
+  for (Worker* w : ctx->ingest_pool) delete w;
+  ctx->ingest_pool.clear();
+}
 
 void FreeIngestRing(nlo_context* ctx) {
   IngestRing& r = ctx->ring;
