@@ -147,7 +147,12 @@ int EnsureIngestPool(nlo_context* ctx, int want) {
   if (ctx->numa_node == -2) ctx->numa_node = DeviceNumaNode(ctx->device);
   const std::vector<int> cpus = NodeCpus(ctx->numa_node);
   while (static_cast<int>(ctx->ingest_pool.size()) < want) {
-    Worker* w = new Worker();
+    Worker* w = nullptr;
+    try {
+      w = new Worker();
+    } catch (...) {  // thread limit of the process / cgroup: gather with the helpers there are
+      break;
+    }
     if (!cpus.empty()) {
       w->Post([cpus]() {
         cpu_set_t set;
@@ -159,7 +164,7 @@ int EnsureIngestPool(nlo_context* ctx, int want) {
     }
     ctx->ingest_pool.push_back(w);
   }
-  return want;
+  return std::min(want, static_cast<int>(ctx->ingest_pool.size()));
 }
 
 int ThreadsFor(const nlo_context* ctx, int64_t n) {
