@@ -67,3 +67,23 @@ def test_product_sources_do_not_touch_the_oracle():
                 if f.endswith(".py"):  # citations in comments are fine; reading the tree is not
                     cleaned = text.replace("/root/reference/nonlinear_optimizer", "")
                     assert "/root/reference" not in cleaned, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/nlo_cuda.h compiles as C99 (-pedantic) with no CUDA, C++ or
+    torch header in sight, and a C program links against the library through it."""
+    from nonlinear_optimizer_for_slam_b200 import build as nlo_build
+    lib = nlo_build.build_cuda()
+    src = tmp_path / "abi.c"
+    src.write_text('#include "nlo_cuda.h"\n'
+                   "int main(void) {\n"
+                   "  nlo_context* ctx = 0;\n"
+                   "  if (nlo_abi_version() != NLO_ABI_VERSION) return 2;\n"
+                   "  if (nlo_visible_device_count() > 0) return 0;\n"
+                   "  return nlo_context_create(0, &ctx) < 0 ? 0 : 3;  /* no GPU: a loud failure, not a fallback */\n"
+                   "}\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", os.path.dirname(lib), "-lnlo_cuda",
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
