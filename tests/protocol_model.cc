@@ -17,6 +17,18 @@
 //                            for all arrivals, sums in CTA order, steps, publishes the state as LL
 //                            words in a SINGLE buffer; the other CTAs poll those words.
 //
+//   model 3  TileRing        the streaming kernel's TMA / mbarrier ring (gn_iteration_kernel): thread 0
+//                            doubles as the producer and keeps STAGES - 1 bulk copies in flight, the
+//                            warps consume a stage after its `full` barrier and release it on its
+//                            `empty` barrier; ring positions are carried incrementally across
+//                            iterations, the first tiles of the NEXT iteration are requested before
+//                            the reduction, a loop that ends early waits for them before the CTA exits,
+//                            and a share that fits the ring stays resident.  Software mbarriers
+//                            (phase parity), a "DMA" thread that lands the copies late, plain stage
+//                            memory: a stage overwritten before every warp released it, a tile read
+//                            before it landed, a wrong ring position or a copy still in flight at exit
+//                            fail the run (or show as a ThreadSanitizer report).
+//
 // A violated invariant shows as a wrong sum (a payload half of another iteration), a poll that
 // never ends (the tag was overwritten: reported as a timeout) or a ThreadSanitizer report.
 // Usage: protocol_model <participants> <iterations> <seed>; prints "PROTOCOL_MODEL_OK" on success.
@@ -26,6 +38,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -65,8 +79,10 @@ void Jitter(uint64_t* rng) {
 // uses slot 0) and a short deadline; a participant one exchange ahead then overwrites words a slower one
 // still waits for, and the run must FAIL.
 bool g_break = false;
+bool g_break_empty = false;  // PROTOCOL_MODEL_BREAK=3: model 3, the producer does not wait for `empty` -- must FAIL
+bool g_break_ring = false;  // PROTOCOL_MODEL_BREAK=2: model 3 without the drain of the prefetch at loop exit -- must FAIL
 struct Deadline {
-  Clock::time_point end = Clock::now() + std::chrono::seconds(g_break ? 3 : 60);
+  Clock::time_point end = Clock::now() + std::chrono::seconds((g_break || g_break_ring || g_break_empty) ? 2 : 60);
   bool Passed() const { return Clock::now() > end; }
 };
 
@@ -74,6 +90,12 @@ std::atomic<int> g_failures{0};
 void FailMsg(const char* what, int who, uint64_t seq) {
   if (g_failures.fetch_add(1) < 5) fprintf(stderr, "protocol_model: %s (participant %d, exchange %llu)\n", what, who,
                                            static_cast<unsigned long long>(seq));
+}
+// model 3: the other warps of a failed run sit in barriers that nobody will complete -- leave at once
+[[noreturn]] void FailAndExit(const char* what, int a, uint64_t b) {
+  fprintf(stderr, "protocol_model: %s (tiles %d, %llu)\n", what, a, static_cast<unsigned long long>(b));
+  fflush(stderr);
+  std::_Exit(1);
 }
 
 // ---------------------------------------------------------------- model 1
@@ -233,6 +255,160 @@ struct LeaderPublish {
   }
 };
 
+
+// ---------------------------------------------------------------- model 3
+struct SoftBarrier {  // mbarrier: arrival count + phase parity; wait(P) returns once the phase of parity P is over
+  std::atomic<int> left{0};
+  std::atomic<uint32_t> parity{0};
+  int count = 1;
+  void Init(int c) { count = c; left.store(c); parity.store(0); }
+  void Arrive() {
+    if (left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      left.store(count, std::memory_order_relaxed);
+      parity.fetch_xor(1u, std::memory_order_release);
+    }
+  }
+  bool TryWait(uint32_t p) const { return parity.load(std::memory_order_acquire) != p; }
+};
+
+struct TileRing {
+  static constexpr int kMaxStages = 4, kStageWords = 16;
+  int warps, stages, my_tiles, iterations, exit_after;  // exit_after: the step of this iteration sets st.done (-1 never)
+  bool solve_mode;
+  SoftBarrier full[kMaxStages], empty[kMaxStages];
+  long stage_data[kMaxStages][kStageWords];  // PLAIN memory: what a bulk copy writes and the warps read
+  // the "TMA engine": copies land late and in order
+  struct Copy { int stage; long content; };
+  std::mutex mu;
+  std::deque<Copy> queue;
+  std::atomic<int> in_flight{0};
+  std::atomic<bool> stop{false};
+  std::atomic<int> done_flag{0};  // st.done, published behind the CTA barrier
+  // a reusable CTA barrier (__syncthreads)
+  std::atomic<int> bar_count{0};
+  std::atomic<int> bar_gen{0};
+  bool failed = false;
+  int issued = 0, awaited = 0;  // bulk copies requested / whose landing warp 0 has waited for (warp 0 only)
+
+  void CtaSync() {
+    const int gen = bar_gen.load(std::memory_order_acquire);
+    if (bar_count.fetch_add(1, std::memory_order_acq_rel) == warps - 1) {
+      bar_count.store(0, std::memory_order_relaxed);
+      bar_gen.fetch_add(1, std::memory_order_release);
+    } else {
+      while (bar_gen.load(std::memory_order_acquire) == gen) std::this_thread::yield();
+    }
+  }
+  bool Wait(SoftBarrier& b, uint32_t parity, const char* what) {
+    Deadline deadline;
+    unsigned polls = 0;
+    while (!b.TryWait(parity)) {
+      if ((++polls & 0x3ffu) == 0) {
+        if (deadline.Passed()) FailAndExit(what, my_tiles, static_cast<uint64_t>(stages));
+        std::this_thread::yield();
+      }
+    }
+    return true;
+  }
+  void Dma() {
+    uint64_t rng = 99;
+    while (true) {
+      Copy c{-1, 0};
+      {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!queue.empty()) { c = queue.front(); queue.pop_front(); }
+      }
+      if (c.stage < 0) {
+        if (stop.load()) return;
+        std::this_thread::yield();
+        continue;
+      }
+      Jitter(&rng);
+      for (int k = 0; k < kStageWords; ++k) stage_data[c.stage][k] = c.content;
+      in_flight.fetch_sub(1, std::memory_order_release);
+      full[c.stage].Arrive();  // complete_tx: the phase of `full` ends when the bytes have landed
+    }
+  }
+  // one warp of the CTA; warp 0 carries thread 0, the producer
+  void Warp(int warp) {
+    const bool producer = warp == 0;
+    uint64_t rng = 7u + static_cast<uint64_t>(warp);
+    int c_stage = 0, p_stage = 0;
+    uint32_t c_phase = 0, p_phase = 0;
+    const bool resident = iterations > 1 && my_tiles <= stages;
+    int prefetched = 0;
+    auto issue_tile = [&](int m, int for_iteration) {
+      const int s = p_stage;
+      const uint32_t phase = p_phase;
+      if (++p_stage == stages) { p_stage = 0; p_phase ^= 1u; }
+      if (!g_break_empty && !Wait(empty[s], phase ^ 1u, "model 3: producer stuck on an empty barrier")) return;
+      in_flight.fetch_add(1, std::memory_order_relaxed);
+      ++issued;
+      std::lock_guard<std::mutex> lock(mu);
+      queue.push_back(Copy{s, 1000L * for_iteration + m});
+    };
+    for (int it = 0; it < iterations; ++it) {
+      if (done_flag.load(std::memory_order_acquire)) break;
+      const bool need_load = !resident || it == 0;
+      if (producer && need_load)
+        for (int m = prefetched; m < stages - 1 && m < my_tiles; ++m) issue_tile(m, it);
+      prefetched = 0;
+      for (int m = 0; m < my_tiles; ++m) {
+        const int s = resident ? m : c_stage;
+        const uint32_t phase = c_phase;
+        if (!resident && ++c_stage == stages) { c_stage = 0; c_phase ^= 1u; }
+        if (need_load) {
+          if (producer && m + stages - 1 < my_tiles) issue_tile(m + stages - 1, it);
+          if (failed || !Wait(full[s], phase, "model 3: a warp stuck on a full barrier")) return;
+          if (producer) ++awaited;
+        }
+        const long expect = 1000L * (resident ? 0 : it) + m;
+        for (int k = 0; k < kStageWords; ++k)
+          if (stage_data[s][k] != expect)
+            FailAndExit("model 3: a warp read a stage that does not hold its tile", m, static_cast<uint64_t>(it));
+        if (!resident) empty[s].Arrive();
+        if ((rng & 3u) == 0) Jitter(&rng);
+        rng = SplitMix(rng);
+      }
+      if (!resident && it + 1 < iterations && solve_mode) {
+        const int ahead = my_tiles < stages - 1 ? my_tiles : stages - 1;
+        if (producer)
+          for (int m = 0; m < ahead; ++m) issue_tile(m, it + 1);
+        prefetched = ahead;
+      }
+      CtaSync();  // reduction ...
+      if (producer && it == exit_after) done_flag.store(1, std::memory_order_release);  // ... and the step
+      CtaSync();
+    }
+    // a prefetch may still be in flight when the loop ends early: let it land before the CTA exits
+    for (int m = 0; m < (g_break_ring ? 0 : prefetched); ++m) {
+      if (!Wait(full[c_stage], c_phase, "model 3: the drain of the prefetch is stuck")) return;
+      if (producer) ++awaited;
+      if (++c_stage == stages) { c_stage = 0; c_phase ^= 1u; }
+    }
+  }
+  bool Run() {
+    for (int s = 0; s < kMaxStages; ++s) {
+      full[s].Init(1);
+      empty[s].Init(warps);
+      for (int k = 0; k < kStageWords; ++k) stage_data[s][k] = -1;
+    }
+    std::thread dma([this]() { Dma(); });
+    std::vector<std::thread> threads;
+    for (int w = 0; w < warps; ++w) threads.emplace_back([this, w]() { Warp(w); });
+    for (auto& t : threads) t.join();
+    // the CTA has exited: nothing may still be on its way into its shared memory
+    const int late = in_flight.load(std::memory_order_acquire);
+    stop.store(true);
+    dma.join();
+    if ((late != 0 || issued != awaited) && !failed) {  // every copy requested has been waited for before the exit
+      FailMsg("model 3: bulk copies not waited for when the CTA exits", my_tiles, static_cast<uint64_t>(issued - awaited));
+      failed = true;
+    }
+    return !failed;
+  }
+};
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -240,7 +416,11 @@ int main(int argc, char** argv) {
   const int iterations = argc > 2 ? atoi(argv[2]) : 2000;
   const uint64_t seed = argc > 3 ? strtoull(argv[3], nullptr, 10) : 1;
   if (n < 1 || n > 1024 || iterations < 1) return 2;
-  if (const char* b = getenv("PROTOCOL_MODEL_BREAK")) g_break = b[0] == '1';
+  if (const char* b = getenv("PROTOCOL_MODEL_BREAK")) {
+    g_break = b[0] == '1';
+    g_break_ring = b[0] == '2';
+    g_break_empty = b[0] == '3';
+  }
   {
     // exchange numbers that cross the 32-bit wrap of the tag (the sequence number is 64-bit on the device,
     // the tag its low 32 bits)
@@ -258,6 +438,28 @@ int main(int argc, char** argv) {
     const double expect = LeaderPublish::Serial(n, iterations);
     for (int c = 0; c < n; ++c)
       if (Bits(model.checksum[static_cast<size_t>(c)]) != Bits(expect)) FailMsg("model 2: final state differs from the serial loop", c, 0);
+  }
+  if (!g_break) {
+    int runs = 0;
+    for (int stages = 2; stages <= TileRing::kMaxStages; ++stages)
+      for (int my_tiles : {0, 1, 2, 3, 4, 5, 9, 23})
+        for (int iters : {1, 2, 5})
+          for (int exit_after : {-1, 0, 2})
+            for (int solve_mode = 0; solve_mode < 2; ++solve_mode) {
+              if (exit_after >= iters) continue;
+              TileRing ring;
+              ring.warps = 4;
+              ring.stages = stages;
+              ring.my_tiles = my_tiles;
+              ring.iterations = iters;
+              ring.exit_after = exit_after;
+              ring.solve_mode = solve_mode != 0;
+              ring.Run();
+              ++runs;
+              if (g_failures.load() != 0) goto ring_done;  // a failed run may leave waits that only end at their deadline
+            }
+  ring_done:
+    if (g_failures.load() == 0) printf("TILE_RING_OK runs=%d\n", runs);
   }
   if (g_failures.load() != 0) {
     fprintf(stderr, "protocol_model: %d failure(s)\n", g_failures.load());

@@ -1,8 +1,9 @@
 """CPU: host-thread models of the kernels' polled exchange protocols (tests/protocol_model.cc) -- the
 LL all-gather with parity double buffering (PeerAllReduce / ReduceAndExchange / GatherLL) and the
-streaming kernel's counter + leader-publishes-state loop -- under random scheduling jitter, across
-the 32-bit wrap of the tag, and under ThreadSanitizer; with a negative control (no double buffer)
-that must fail.  racecheck being unavailable on the GPU pool, this is where the protocols' logic is
+streaming kernel's counter + leader-publishes-state loop, and the TMA / mbarrier tile ring with its
+cross-iteration prefetch, early-exit drain and resident mode -- under random scheduling jitter, across
+the 32-bit wrap of the tag, and under ThreadSanitizer; with negative controls (no double buffer, no
+drain) that must fail.  racecheck being unavailable on the GPU pool, this is where the protocols' logic is
 exercised on its own; the kernels themselves are covered by the bitwise-repeatability GPU tests."""
 import os
 import subprocess
@@ -30,6 +31,21 @@ def test_protocols_hold_under_jitter(model, participants, iterations, seed):
                          timeout=300)
     assert out.returncode == 0, out.stderr
     assert "PROTOCOL_MODEL_OK" in out.stdout
+    assert "TILE_RING_OK runs=336" in out.stdout   # stages 2-4 x tiles 0-23 x iterations x early exit x mode
+
+
+def test_negative_control_without_the_prefetch_drain_fails(model):
+    env = dict(os.environ, PROTOCOL_MODEL_BREAK="2")
+    out = subprocess.run([model, "2", "10", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 1
+    assert "bulk copies not waited for" in out.stderr
+
+
+def test_negative_control_producer_ignoring_the_empty_barrier_fails(model):
+    env = dict(os.environ, PROTOCOL_MODEL_BREAK="3")
+    out = subprocess.run([model, "2", "10", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 1
+    assert "model 3" in out.stderr
 
 
 def test_negative_control_without_the_double_buffer_fails(model):
